@@ -1,0 +1,45 @@
+/* lpb_functor.h -- problem-definition interface of lpopc-b200 (device functors).
+ *
+ * This header is the B200-native mirror of the reference's problem-definition
+ * interface `Lpopc::FunctionWrapper` (Lpopc/src/Core/LpFunctionWrapper.h:50-69):
+ *
+ *   reference virtual (whole mesh, Armadillo)          functor member (ONE node / endpoint)
+ *   ------------------------------------------------   ------------------------------------
+ *   MayerCost(SolCost&, double&)                        mayer(c, phase, t0, x0, tf, xf)
+ *   LagrangeCost(SolCost&, vec&)        [N values]      lagrange(c, phase, t, x, u)
+ *   DaeFunction(SolDae&, mat&, mat&)    [N x ns|np]     dae(c, phase, t, x, u, f, path)
+ *   EventFunction(SolEvent&, vec&)                      event(c, phase, t0, x0, tf, xf, e)
+ *   LinkFunction(SolLink&, vec&)                        link(c, xf_left, x0_right, out)
+ *   Deriv* (analytic, optional)                         ddae / dlagrange (HAS_ANALYTIC)
+ *
+ * The reference requires every user function to be pointwise in the node index
+ * (row k of the output depends only on row k of the inputs; the finite-difference
+ * scheme in LpFiniteDifferenceDerive.cpp:194-324 and the whole sparsity pattern
+ * assume it).  Here that requirement is the interface: a functor sees one node.
+ * `phase` is 1-based like `phase_num_` (LpNLPWrapper.cpp:107).
+ *
+ * A functor set is a plain struct with compile-time sizes shared by all phases
+ * (NS states, NC controls, NPATH path constraints; NE_MAX/NL_MAX upper bounds for
+ * events per phase / links per pair) and a POD `Consts` block of doubles that the
+ * host passes by value to every kernel (it lands in the constant bank).
+ *
+ * Numerics contract (see DESIGN.md "bit-exact user functions"): the same header
+ * is compiled by g++ -ffp-contract=off (oracle) and nvcc --fmad=false (device);
+ * functors must only use + - * / sqrt fabs and the lpb_det_* functions from
+ * lpb_detmath.h, which makes f(x) bit-identical on host and device and so keeps
+ * forward-difference quotients (cancellation-amplified by 1/h ~ 1e6) within the
+ * 1e-12 parity bound.  No fast-math: NaN must propagate (dependency probe,
+ * LpDerivDependciesChecker.cpp:61-94).
+ */
+#ifndef LPB_FUNCTOR_H
+#define LPB_FUNCTOR_H
+
+#if defined(__CUDACC__)
+#define LPB_HD __host__ __device__ __forceinline__
+#else
+#define LPB_HD inline
+#endif
+
+#include "lpb_detmath.h"
+
+#endif /* LPB_FUNCTOR_H */

@@ -1,0 +1,151 @@
+/* lpopc_b200.h -- C ABI of the B200-native Radau-pseudospectral transcription.
+ *
+ * Drop-in boundary for lpopc's NLP evaluation path.  The entry points below are
+ * what a binding to the reference's `Ipopt::TNLP` adapter would call; each one
+ * cites the reference interface it replaces.  Plain pointers and sizes only: no
+ * C++ types, no exceptions across the ABI.  Every function returns LPB_OK (0) or
+ * a negative error code; lpb_last_error() gives the message.
+ *
+ * Conventions copied from the reference boundary:
+ *   - the caller owns every array; the callee fills in place;
+ *   - triplets are 0-based (TNLP::C_STYLE, LpopcIpopt.cpp:22), duplicates are
+ *     part of the contract (IPOPT sums them);
+ *   - eval_jac_g / eval_h with values == NULL return the structure
+ *     (LpopcIpopt.cpp:156-164, :187-195);
+ *   - m includes the linear rows (LpopcIpopt.cpp:14);
+ *   - one handle = one host thread (the reference is not re-entrant either).
+ * The hot path has no CPU fallback: if no CUDA device is usable, lpb_create
+ * fails with LPB_ERR_CUDA.
+ */
+#ifndef LPOPC_B200_H
+#define LPOPC_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LPB_OK 0
+#define LPB_ERR_INVALID (-1)     /* bad argument / inconsistent description      */
+#define LPB_ERR_UNSUPPORTED (-2) /* e.g. nparameters > 0     */
+#define LPB_ERR_CUDA (-3)        /* CUDA runtime error / no device               */
+#define LPB_ERR_STATE (-4)       /* call order (mesh not set, ...)               */
+#define LPB_ERR_UNKNOWN_FUNCTOR (-5)
+
+#define LPB_DERIVE_FINITE_DIFFERENCE 0 /* "first-derive" option, LpOptDerive.hpp:27-37 */
+#define LPB_DERIVE_ANALYTIC 1
+
+/* One phase: mirrors Lpopc::Phase (LpOptimalProblem.hpp:30-240).  State limits
+ * carry three values per state like Lpopc::Limit (initial node, interior nodes,
+ * terminal point; LpBoundsChecker.cpp:51-75). */
+typedef struct lpb_phase_desc {
+    int nstates, ncontrols, nparameters, npaths, nevents;
+    const double* state_min0; const double* state_min; const double* state_minf; /* [nstates] */
+    const double* state_max0; const double* state_max; const double* state_maxf; /* [nstates] */
+    const double* control_min; const double* control_max;                         /* [ncontrols] */
+    const double* path_min; const double* path_max;                               /* [npaths] */
+    const double* event_min; const double* event_max;                             /* [nevents] */
+    double t0_min, t0_max, tf_min, tf_max; /* Phase::SetTimeMin/Max */
+    int has_duration;                      /* Phase::SetDuration   */
+    double duration_min, duration_max;
+} lpb_phase_desc;
+
+/* One linkage pair: mirrors Lpopc::Linkage (LpOptimalProblem.hpp:242-281);
+ * left_phase/right_phase are 1-based like the Linkage constructor. */
+typedef struct lpb_link_desc {
+    int left_phase, right_phase;
+    int nlinks;
+    const double* link_min; const double* link_max; /* [nlinks] */
+} lpb_link_desc;
+
+/* Whole problem: mirrors Lpopc::OptimalProblem + the options that reach the hot
+ * path ("finite-difference-tol", "first-derive"; LpOptDerive.hpp:27-37). */
+typedef struct lpb_problem_desc {
+    const char* functor; /* name of a registered functor set (include/problems/) */
+    int nphases;
+    const lpb_phase_desc* phases;
+    int nlinkpairs;
+    const lpb_link_desc* links;
+    const double* consts; /* functor constants, sizeof(Functor::Consts)/8 doubles */
+    int nconsts;
+    double fd_tol;    /* 0 -> reference default 1e-6 */
+    int first_derive; /* LPB_DERIVE_* */
+} lpb_problem_desc;
+
+typedef struct lpb_handle lpb_handle;
+
+/* Replaces: LpopcAlgorithm::Initialized object wiring (LpLpopcAlgorithm.cpp:157-246). */
+int lpb_create(const lpb_problem_desc* desc, lpb_handle** out);
+int lpb_destroy(lpb_handle* h);
+const char* lpb_last_error(const lpb_handle* h); /* h may be NULL: last create error */
+
+/* Replaces: Phase::SetMeshPoints / SetNodesPerInterval + MeshRefiner::SetAndCheckMesh
+ * (LpMeshRefiner.cpp:10-61).  phase is 0-based; meshpoints has K+1 entries spanning
+ * [-1, 1]; nodes_per_interval has K entries (each >= 2). */
+int lpb_set_mesh(lpb_handle* h, int phase, int K, const double* meshpoints, const int* nodes_per_interval);
+
+/* Replaces: GetSizes/GetBounds/GetGuess PS-table fill + RefreshSparsity for a new
+ * mesh (LpLpopcAlgorithm.cpp:36-45, LpGuessChecker.cpp:110-122, LpNLPWrapper.hpp:89).
+ * Uploads the LGR tables and rebuilds every index map / triplet array on the GPU.
+ * Called implicitly by lpb_get_nlp_info when the mesh changed. */
+int lpb_refresh(lpb_handle* h);
+
+/* Replaces: LpopcIpopt::get_nlp_info (LpopcIpopt.cpp:11-25). */
+int lpb_get_nlp_info(lpb_handle* h, int* n, int* m, int* nnz_jac_g, int* nnz_h_lag);
+/* Replaces: LpopcIpopt::get_bounds_info (LpopcIpopt.cpp:27-83). */
+int lpb_get_bounds_info(lpb_handle* h, double* x_l, double* x_u, double* g_l, double* g_u);
+
+/* Replaces: LpopcIpopt::eval_f -> NLPWrapper::GetObjFun (LpopcIpopt.cpp:106, LpNLPWrapper.cpp:863). */
+int lpb_eval_f(lpb_handle* h, const double* x, double* obj_value);
+/* Replaces: eval_grad_f -> GetObjGrad (LpopcIpopt.cpp:118, LpNLPWrapper.cpp:940). */
+int lpb_eval_grad_f(lpb_handle* h, const double* x, double* grad_f);
+/* Replaces: eval_g -> GetAllCons (LpopcIpopt.cpp:135, LpNLPWrapper.cpp:34). */
+int lpb_eval_g(lpb_handle* h, const double* x, double* g);
+/* Replaces: eval_jac_g -> GetConsSparsity / GetConsJacbi (LpopcIpopt.cpp:152,
+ * LpNLPWrapper.cpp:1550, :230).  values == NULL -> fill iRow/jCol only. */
+int lpb_eval_jac_g(lpb_handle* h, const double* x, int* iRow, int* jCol, double* values);
+/* Replaces: eval_h -> GetHessainSparsity / GetHessainValue (LpopcIpopt.cpp:183,
+ * LpNLPWrapper.cpp:2354-2376, LpHessian.cpp:878, :2510). */
+int lpb_eval_h(lpb_handle* h, const double* x, double obj_factor, const double* lambda,
+               int* iRow, int* jCol, double* values);
+/* Fused eval_g + eval_jac_g(values) in one pass (the headline "defect+Jacobian"
+ * evaluation; one H2D of x, one D2H of g and values). */
+int lpb_eval_g_jac(lpb_handle* h, const double* x, double* g, double* values);
+
+/* Replaces: DeriveDependicieshecker::GetDependiciesForJacobiInEveryPhase
+ * (LpDerivDependciesChecker.cpp:10-94): NaN-probe of the dae functor at node 1 of
+ * x_guess; the mask feeds the Hessian pattern only.  If it
+ * is never called the mask is all-ones.  dep_out (optional) receives, per phase,
+ * (ns+np) x (ns+nc) 0/1 values, column-major, phases concatenated. */
+int lpb_probe_dependencies(lpb_handle* h, const double* x_guess, int* dep_out);
+
+/* ---- batched independent instances (MPC-style; BASELINE config 4) ----------
+ * nbatch instances share problem, mesh, tables and pattern; instance b uses
+ * x[b*n .. b*n+n).  Host-pointer versions copy H2D/D2H around the kernels. */
+int lpb_eval_f_batch(lpb_handle* h, int nbatch, const double* x, double* obj_values);
+int lpb_eval_grad_f_batch(lpb_handle* h, int nbatch, const double* x, double* grad_f);
+int lpb_eval_g_jac_batch(lpb_handle* h, int nbatch, const double* x, double* g, double* values);
+int lpb_eval_h_batch(lpb_handle* h, int nbatch, const double* x, const double* obj_factor,
+                     const double* lambda, double* values);
+
+/* ---- device-resident entry points (pointers are CUDA device pointers) ------
+ * Asynchronous on the handle's stream; no host synchronisation.  g / values /
+ * grad may be NULL to skip that output. */
+int lpb_set_stream(lpb_handle* h, void* cuda_stream);
+int lpb_eval_f_dev(lpb_handle* h, int nbatch, const double* d_x, double* d_obj);
+int lpb_eval_grad_f_dev(lpb_handle* h, int nbatch, const double* d_x, double* d_grad);
+int lpb_eval_g_jac_dev(lpb_handle* h, int nbatch, const double* d_x, double* d_g, double* d_values);
+int lpb_eval_h_dev(lpb_handle* h, int nbatch, const double* d_x, const double* d_obj_factor,
+                   const double* d_lambda, double* d_values);
+int lpb_structure_dev(lpb_handle* h, const int** d_jac_iRow, const int** d_jac_jCol,
+                      const int** d_h_iRow, const int** d_h_jCol);
+
+/* Tuning / introspection (not part of the reference boundary). */
+int lpb_set_option_int(lpb_handle* h, const char* name, int value);
+long long lpb_kernel_launch_count(const lpb_handle* h); /* kernels launched so far */
+int lpb_num_functors(void);
+const char* lpb_functor_name(int i);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LPOPC_B200_H */

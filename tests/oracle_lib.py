@@ -1,0 +1,183 @@
+"""ctypes binding of the CPU oracle (oracle/liblpopc_oracle.so) -- TEST INFRASTRUCTURE.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg
+may import this.  Builds the library with oracle/Makefile when it is missing.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(ROOT, "oracle", "liblpopc_oracle.so")
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+
+def build_oracle(force=False):
+    srcs = [os.path.join(ROOT, "oracle", f) for f in os.listdir(os.path.join(ROOT, "oracle")) if f.endswith((".cpp", ".hpp"))]
+    hdrs = []
+    for d in (os.path.join(ROOT, "include"), os.path.join(ROOT, "include", "problems")):
+        hdrs += [os.path.join(d, f) for f in os.listdir(d) if f.endswith(".h")]
+    stale = force or not os.path.exists(LIB_PATH)
+    if not stale:
+        t = os.path.getmtime(LIB_PATH)
+        stale = any(os.path.getmtime(s) > t for s in srcs + hdrs)
+    if stale:
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, capture_output=True)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build_oracle()
+        _lib = C.CDLL(LIB_PATH)
+        _lib.lpo_create.restype = C.c_void_p
+        _lib.lpo_last_error.restype = C.c_char_p
+        for name in ("lpo_destroy", "lpo_last_error", "lpo_set_mesh", "lpo_refresh", "lpo_get_nlp_info", "lpo_get_bounds_info",
+                     "lpo_eval_f", "lpo_eval_grad_f", "lpo_eval_g", "lpo_eval_jac_g", "lpo_eval_h", "lpo_probe_dependencies",
+                     "lpo_get_tables", "lpo_get_coo", "lpo_eval_g_jac_batch"):
+            getattr(_lib, name).argtypes = None
+    return _lib
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    return a.ctypes.data_as(_ip)
+
+
+class Oracle:
+    """CPU restatement of the reference path for one OptimalProblem."""
+
+    def __init__(self, op):
+        self.op = op
+        desc, self._keep = op.to_desc()
+        err = C.create_string_buffer(512)
+        self.h = C.c_void_p(lib().lpo_create(C.byref(desc), err, 512))
+        if not self.h:
+            raise RuntimeError("oracle create failed: " + err.value.decode())
+        for ip, p in enumerate(op.phases):
+            if p.meshpoints:
+                self.set_mesh(ip, p.meshpoints, p.nodesperinterval)
+        self._check(lib().lpo_refresh(self.h))
+        self.n, self.m, self.nnz_jac, self.nnz_h = self.nlp_info()
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError("oracle: " + lib().lpo_last_error(self.h).decode())
+
+    def close(self):
+        if self.h:
+            lib().lpo_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_mesh(self, phase, meshpoints, nodes):
+        mp = np.ascontiguousarray(meshpoints, dtype=np.float64)
+        nd = np.ascontiguousarray(nodes, dtype=np.int32)
+        self._check(lib().lpo_set_mesh(self.h, C.c_int(phase), C.c_int(len(nd)), _d(mp), _i(nd)))
+
+    def refresh(self):
+        self._check(lib().lpo_refresh(self.h))
+        self.n, self.m, self.nnz_jac, self.nnz_h = self.nlp_info()
+
+    def nlp_info(self):
+        v = [C.c_int() for _ in range(4)]
+        self._check(lib().lpo_get_nlp_info(self.h, *[C.byref(x) for x in v]))
+        return tuple(x.value for x in v)
+
+    def bounds(self):
+        xl, xu = np.empty(self.n), np.empty(self.n)
+        gl, gu = np.empty(self.m), np.empty(self.m)
+        self._check(lib().lpo_get_bounds_info(self.h, _d(xl), _d(xu), _d(gl), _d(gu)))
+        return xl, xu, gl, gu
+
+    def eval_f(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        f = C.c_double()
+        self._check(lib().lpo_eval_f(self.h, _d(x), C.byref(f)))
+        return f.value
+
+    def eval_grad_f(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        g = np.empty(self.n)
+        self._check(lib().lpo_eval_grad_f(self.h, _d(x), _d(g)))
+        return g
+
+    def eval_g(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        g = np.empty(self.m)
+        self._check(lib().lpo_eval_g(self.h, _d(x), _d(g)))
+        return g
+
+    def jac_structure(self):
+        i, j = np.empty(self.nnz_jac, dtype=np.int32), np.empty(self.nnz_jac, dtype=np.int32)
+        self._check(lib().lpo_eval_jac_g(self.h, None, _i(i), _i(j), None))
+        return i, j
+
+    def eval_jac_g(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        v = np.empty(self.nnz_jac)
+        self._check(lib().lpo_eval_jac_g(self.h, _d(x), None, None, _d(v)))
+        return v
+
+    def h_structure(self):
+        i, j = np.empty(self.nnz_h, dtype=np.int32), np.empty(self.nnz_h, dtype=np.int32)
+        self._check(lib().lpo_eval_h(self.h, None, C.c_double(0), None, _i(i), _i(j), None))
+        return i, j
+
+    def eval_h(self, x, sigma, lam):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        lam = np.ascontiguousarray(lam, dtype=np.float64)
+        v = np.empty(self.nnz_h)
+        self._check(lib().lpo_eval_h(self.h, _d(x), C.c_double(sigma), _d(lam), None, None, _d(v)))
+        return v
+
+    def probe_dependencies(self, xguess):
+        x = np.ascontiguousarray(xguess, dtype=np.float64)
+        tot = sum((len(p.statemin) + len(p.pathmin)) * (len(p.statemin) + len(p.controlmin)) for p in self.op.phases)
+        dep = np.zeros(tot, dtype=np.int32)
+        self._check(lib().lpo_probe_dependencies(self.h, _d(x), _i(dep)))
+        self.n, self.m, self.nnz_jac, self.nnz_h = self.nlp_info()
+        return dep
+
+    def tables(self, phase):
+        N = self.op.phases[phase].GetTotalNodes()
+        pts, w = np.empty(N), np.empty(N)
+        nD, nDiag, nDoff = C.c_int(), C.c_int(), C.c_int()
+        self._check(lib().lpo_get_tables(self.h, C.c_int(phase), _d(pts), _d(w), C.byref(nD), C.byref(nDiag), C.byref(nDoff)))
+        out = {"points": pts, "weights": w}
+        for which, (name, cnt) in enumerate((("D", nD.value), ("Diag", nDiag.value), ("Doffdiag", nDoff.value))):
+            r, c, v = np.empty(cnt, dtype=np.int32), np.empty(cnt, dtype=np.int32), np.empty(cnt)
+            self._check(lib().lpo_get_coo(self.h, C.c_int(phase), C.c_int(which), _i(r), _i(c), _d(v)))
+            out[name] = (r, c, v)
+        return out
+
+    def eval_g_jac_batch(self, x, nthreads=1, want_g=True, want_jac=True):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        nb = x.size // self.n
+        g = np.empty((nb, self.m)) if want_g else None
+        v = np.empty((nb, self.nnz_jac)) if want_jac else None
+        self._check(lib().lpo_eval_g_jac_batch(self.h, C.c_int(nb), _d(x), _d(g) if want_g else None, _d(v) if want_jac else None, C.c_int(nthreads)))
+        return g, v
+
+
+def detmath(which, x):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.empty_like(x)
+    lib().lpo_detmath(C.c_int(which), C.c_int(x.size), _d(x), _d(y))
+    return y
