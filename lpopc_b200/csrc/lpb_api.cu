@@ -1,0 +1,832 @@
+// lpb_api.cu -- handle, mesh refresh (tables + GPU index-map construction) and the C ABI of
+// include/lpopc_b200.h.
+//
+// Replaces, for the hot path only:
+//   LpopcIpopt (TNLP marshalling)                 Lpopc/src/Core/LpopcIpopt.cpp:11-218
+//   GetSize / GetBounds                           LpSizeChecker.cpp:13-152, LpBoundsChecker.cpp:13-348
+//   PS-table fill + RefreshSparsity per mesh      LpGuessChecker.cpp:110-122, LpNLPWrapper.hpp:89
+//   GetConsSparsity / GetHessianSparsity          LpNLPWrapper.cpp:1550-1578, LpHessian.cpp:2510-2599
+// There is no CPU fallback: every evaluation entry point launches the CUDA kernels of
+// lpb_kernels.cuh / lpb_hessian.cuh; without a usable device lpb_create fails.
+#include "../../include/lpopc_b200.h"
+#include "lpb_device.hpp"
+#include "lpb_structure.hpp"
+#include "lpb_tables.hpp"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+// ---- functor registry ---------------------------------------------------------------------
+#define LPB_REGISTRY(X)  \
+    X(LpbHypersensitive) \
+    X(LpbBrysonDenham)   \
+    X(LpbLaunch)         \
+    X(LpbOrbitRaising)   \
+    X(LpbBrachistochrone)\
+    X(LpbQuadrotor)      \
+    X(LpbCartpole)       \
+    X(LpbSynthetic20)
+#define LPB_DECL(T) extern "C" const lpb::FunctorVTable* lpb_vtable_##T();
+LPB_REGISTRY(LPB_DECL)
+#undef LPB_DECL
+
+namespace lpb {
+
+const FunctorVTable* const* functor_registry(int* count)
+{
+#define LPB_GET(T) lpb_vtable_##T(),
+    static const FunctorVTable* const tab[] = {LPB_REGISTRY(LPB_GET)};
+#undef LPB_GET
+    *count = (int)(sizeof(tab) / sizeof(tab[0]));
+    return tab;
+}
+
+struct CudaError : std::runtime_error {
+    explicit CudaError(const std::string& s) : std::runtime_error(s) {}
+};
+struct ApiError : std::runtime_error {
+    int code;
+    ApiError(int c, const std::string& s) : std::runtime_error(s), code(c) {}
+};
+
+static void ck(cudaError_t e, const char* what)
+{
+    if (e != cudaSuccess) throw CudaError(std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CK(x) ck((x), #x)
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    DevBuf() {}
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), cap(o.cap) { o.p = nullptr; o.cap = 0; }
+    ~DevBuf() { if (p) cudaFree(p); }
+    void reserve(size_t n)
+    {
+        if (n <= cap) return;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        CK(cudaMalloc((void**)&p, n * sizeof(T)));
+        cap = n;
+    }
+    void upload(const std::vector<T>& v, cudaStream_t st)
+    {
+        reserve(v.size() ? v.size() : 1);
+        if (!v.empty()) CK(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+    }
+};
+
+// ---- GPU structure kernels ------------------------------------------------------------------
+// one thread per triplet: segment lookup + closed-form (row, col) (lpb_structure.hpp), coalesced
+// int32 stores.  Re-run on every mesh change (RefreshSparsity, LpNLPWrapper.hpp:89).
+__global__ void __launch_bounds__(256)
+k_jac_structure(const __grid_constant__ Layout L, const __grid_constant__ LayoutTables T, int* __restrict__ iRow, int* __restrict__ jCol)
+{
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= L.nnz_jac) return;
+    int row = -1, col = -1;
+    jac_entry(L, T, e, &row, &col);
+    iRow[e] = row;
+    jCol[e] = col;
+}
+
+__global__ void __launch_bounds__(256)
+k_hess_structure(const __grid_constant__ Layout L, const __grid_constant__ LayoutTables T, int* __restrict__ iRow, int* __restrict__ jCol)
+{
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= L.nnz_h) return;
+    int row = -1, col = -1;
+    hess_entry(L, T, e, &row, &col);
+    iRow[e] = row;
+    jCol[e] = col;
+}
+
+// ---- ordered compaction (flag / scan / scatter) of the composite Radau matrices -------------
+// The reference stores D, Diag and Doffdiag as COO after Sparse -> Find -> Sparse
+// (RPMGenerator.cpp:178-180): entries in interval-major, column-major-in-block order with exact
+// zeros dropped (LpSparseMatrix.cpp:240-272).  The dense blocks live in HBM; these kernels
+// produce the compacted Doffdiag triplets (rows/cols local to the phase) and the compacted
+// Diag values in that exact order.
+constexpr int kCompactThreads = 256, kCompactPer = 4, kCompactTile = kCompactThreads * kCompactPer;
+
+__global__ void __launch_bounds__(kCompactThreads)
+k_compact_count(const __grid_constant__ CompactDev c, int* __restrict__ counts)
+{
+    __shared__ int sm[kCompactThreads];
+    const long long base = (long long)blockIdx.x * kCompactTile + (long long)threadIdx.x * kCompactPer;
+    int cnt = 0;
+    for (int q = 0; q < kCompactPer; ++q) {
+        int a, b; double v;
+        if (base + q < c.total && compact_candidate(c, base + q, &a, &b, &v)) ++cnt;
+    }
+    sm[threadIdx.x] = cnt;
+    __syncthreads();
+    for (int s = kCompactThreads / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) sm[threadIdx.x] += sm[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) counts[blockIdx.x] = sm[0];
+}
+
+// single block: exclusive scan of the tile counts in place, total at counts[nblocks]
+__global__ void __launch_bounds__(1024) k_compact_scan(int* __restrict__ counts, int nblocks)
+{
+    __shared__ int sm[1024];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nblocks; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int v = i < nblocks ? counts[i] : 0;
+        sm[threadIdx.x] = v;
+        __syncthreads();
+        for (int off = 1; off < 1024; off <<= 1) { // Hillis-Steele inclusive scan
+            const int t = (int)threadIdx.x >= off ? sm[threadIdx.x - off] : 0;
+            __syncthreads();
+            sm[threadIdx.x] += t;
+            __syncthreads();
+        }
+        if (i < nblocks) counts[i] = carry + sm[threadIdx.x] - v;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += sm[1023];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) counts[nblocks] = carry;
+}
+
+__global__ void __launch_bounds__(kCompactThreads)
+k_compact_scatter(const __grid_constant__ CompactDev c, const int* __restrict__ counts,
+                  int* __restrict__ out_a, int* __restrict__ out_b, double* __restrict__ out_v)
+{
+    __shared__ int sm[kCompactThreads];
+    const long long base = (long long)blockIdx.x * kCompactTile + (long long)threadIdx.x * kCompactPer;
+    int a[kCompactPer], b[kCompactPer];
+    double v[kCompactPer];
+    bool keep[kCompactPer];
+    int cnt = 0;
+    for (int q = 0; q < kCompactPer; ++q) {
+        keep[q] = base + q < c.total && compact_candidate(c, base + q, &a[q], &b[q], &v[q]);
+        cnt += keep[q] ? 1 : 0;
+    }
+    sm[threadIdx.x] = cnt;
+    __syncthreads();
+    for (int off = 1; off < kCompactThreads; off <<= 1) {
+        const int t = (int)threadIdx.x >= off ? sm[threadIdx.x - off] : 0;
+        __syncthreads();
+        sm[threadIdx.x] += t;
+        __syncthreads();
+    }
+    int pos = counts[blockIdx.x] + sm[threadIdx.x] - cnt;
+    for (int q = 0; q < kCompactPer; ++q)
+        if (keep[q]) {
+            if (out_a) { out_a[pos] = a[q]; out_b[pos] = b[q]; }
+            out_v[pos] = v[q];
+            ++pos;
+        }
+}
+
+// constant Jacobian segment: Doffdiag values repeated per state (LpNLPWrapper.cpp:715-718);
+// one thread per output value, streaming stores
+__global__ void __launch_bounds__(256)
+k_fill_const(const __grid_constant__ ProblemDev pd, int nbatch, double* __restrict__ vals)
+{
+    const long long per = pd.ctot;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= per * nbatch) return;
+    const int b = (int)(gid / per);
+    const long long e = gid - (long long)b * per;
+    int p = 0;
+    while (p + 1 < pd.P && e >= pd.ph[p + 1].c0 - pd.ph[0].c0) ++p;
+    const long long loc = e - (pd.ph[p].c0 - pd.ph[0].c0);
+    const int idx = (int)(loc % pd.ph[p].ndoff);
+    __stcs(vals + (size_t)b * pd.nnz_jac + pd.ph[0].c0 + e, pd.ph[p].doff_vals[idx]);
+}
+
+int launch_fill_const(const ProblemDev& pd, cudaStream_t st, int nbatch, double* vals)
+{
+    const long long tot = pd.ctot * nbatch;
+    if (tot <= 0) return 0;
+    k_fill_const<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(pd, nbatch, vals);
+    return 1;
+}
+
+} // namespace lpb
+
+using namespace lpb;
+
+// ---- handle ---------------------------------------------------------------------------------
+struct PhaseHost {
+    int ns = 0, nc = 0, nq = 0, np = 0, ne = 0;
+    std::vector<double> smin0, smin, sminf, smax0, smax, smaxf, cmin, cmax, pmin, pmax, emin, emax;
+    double t0_min = 0, t0_max = 0, tf_min = 0, tf_max = 0;
+    int has_duration = 0;
+    double dur_min = 0, dur_max = 0;
+    std::vector<double> mesh;
+    std::vector<int> nodes;
+    PhaseTables tab;
+    std::vector<int> dep; // (ns+np) x (ns+nc), column-major, 0/1
+    std::vector<int> pair_a, pair_b, hblk;
+    DevBuf<double> d_tau, d_w, d_ddiag, d_dblocks, d_doff_vals;
+    DevBuf<int> d_node_interval, d_int_row0, d_int_n, d_doff_a, d_doff_b, d_hblk, d_pair_a, d_pair_b, d_counts;
+    DevBuf<long long> d_int_d0;
+};
+
+struct LinkHost {
+    int left = 0, right = 0; // 0-based
+    std::vector<double> lmin, lmax;
+};
+
+struct lpb_handle {
+    const FunctorVTable* vt = nullptr;
+    std::vector<double> consts;
+    std::vector<PhaseHost> ph;
+    std::vector<LinkHost> lk;
+    double tol = 1e-6;
+    int first_derive = 0;
+    bool fresh = false;
+    ProblemDev pd;
+    Layout lay;
+    LayoutTables ltab;
+    LaunchOpts opts;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    long long launches = 0;
+    std::string err;
+    // structure
+    DevBuf<int> d_jI, d_jJ, d_hI, d_hJ;
+    DevBuf<HessEntry> d_eent, d_lent;
+    std::vector<HessEntry> eent, lent;
+    // evaluation staging
+    DevBuf<double> d_x, d_g, d_vals, d_grad, d_lambda, d_sigma, d_hvals, d_f, d_scratch;
+    DevBuf<int> d_dep;
+    lpb_handle() { std::memset(&pd, 0, sizeof pd); std::memset(&lay, 0, sizeof lay); std::memset(&ltab, 0, sizeof ltab); std::memset(&opts, 0, sizeof opts); }
+    ~lpb_handle()
+    {
+        if (own_stream && stream) cudaStreamDestroy(stream);
+    }
+};
+
+static std::string g_create_error;
+
+static std::string fmt(const char* f, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, f);
+    vsnprintf(buf, sizeof buf, f, ap);
+    va_end(ap);
+    return buf;
+}
+
+#define LPB_API_BEGIN(h)                                            \
+    if (!(h)) return LPB_ERR_INVALID;                               \
+    try {
+#define LPB_API_END(h)                                              \
+    return LPB_OK;                                                  \
+    }                                                               \
+    catch (const ApiError& e) { (h)->err = e.what(); return e.code; } \
+    catch (const CudaError& e) { (h)->err = e.what(); return LPB_ERR_CUDA; } \
+    catch (const std::exception& e) { (h)->err = e.what(); return LPB_ERR_INVALID; }
+
+static void copy_vec(std::vector<double>& dst, const double* src, int n, const char* what)
+{
+    if (n > 0 && !src) throw ApiError(LPB_ERR_INVALID, std::string("null bound array: ") + what);
+    dst.assign(src, src + (n > 0 ? n : 0));
+}
+
+static int run_compaction(lpb_handle* h, PhaseHost& p, int mode, int* out_a, int* out_b, double* out_v, bool count_only)
+{
+    CompactDev c;
+    c.mode = mode;
+    c.K = p.tab.K; c.N = p.tab.N;
+    c.total = mode == 1 ? (long long)p.tab.N : (long long)p.tab.dblocks.size();
+    c.dblocks = p.d_dblocks.p; c.int_d0 = p.d_int_d0.p; c.int_row0 = p.d_int_row0.p; c.int_n = p.d_int_n.p;
+    c.node_interval = p.d_node_interval.p;
+    const int nblocks = (int)((c.total + kCompactTile - 1) / kCompactTile);
+    p.d_counts.reserve((size_t)nblocks + 1);
+    if (count_only) {
+        k_compact_count<<<nblocks, kCompactThreads, 0, h->stream>>>(c, p.d_counts.p);
+        k_compact_scan<<<1, 1024, 0, h->stream>>>(p.d_counts.p, nblocks);
+        h->launches += 2;
+        int total = 0;
+        CK(cudaMemcpyAsync(&total, p.d_counts.p + nblocks, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        return total;
+    }
+    k_compact_scatter<<<nblocks, kCompactThreads, 0, h->stream>>>(c, p.d_counts.p, out_a, out_b, out_v);
+    h->launches += 1;
+    return 0;
+}
+
+// GetSizes -> GetBounds -> GetGuess(PS fill) -> RefreshSparsity of one mesh (LpLpopcAlgorithm.cpp:36-45)
+static void refresh(lpb_handle* h)
+{
+    const int P = (int)h->ph.size(), Lp = (int)h->lk.size();
+    const int ns = h->vt->NS, nc = h->vt->NC, np = h->vt->NPATH;
+    ProblemDev& pd = h->pd;
+    Layout& L = h->lay;
+    LayoutTables& T = h->ltab;
+    std::memset(&pd, 0, sizeof pd);
+    std::memset(&L, 0, sizeof L);
+    std::memset(&T, 0, sizeof T);
+    L.P = P; L.Lp = Lp; L.ns = ns; L.nc = nc; L.np = np;
+
+    // tables (host fp64, RPMGenerator.cpp:43-105), upload, compacted Diag / Doffdiag on the GPU
+    for (int ip = 0; ip < P; ++ip) {
+        PhaseHost& p = h->ph[ip];
+        if (p.mesh.size() != p.nodes.size() + 1)
+            throw ApiError(LPB_ERR_INVALID, fmt("Number of nodesPerInterval must match number of mesh intervals in phase%d", ip + 1));
+        try {
+            build_phase_tables((int)p.nodes.size(), p.mesh.data(), p.nodes.data(), p.tab);
+        } catch (const std::exception& e) {
+            throw ApiError(LPB_ERR_INVALID, std::string(e.what()) + fmt(" in phase%d", ip + 1));
+        }
+        p.d_tau.upload(p.tab.tau, h->stream);
+        p.d_w.upload(p.tab.w, h->stream);
+        p.d_node_interval.upload(p.tab.node_interval, h->stream);
+        p.d_int_row0.upload(p.tab.int_row0, h->stream);
+        p.d_int_n.upload(p.tab.int_n, h->stream);
+        p.d_int_d0.upload(p.tab.int_d0, h->stream);
+        p.d_dblocks.upload(p.tab.dblocks, h->stream);
+        const int N = p.tab.N;
+        if (N < 2) throw ApiError(LPB_ERR_INVALID, fmt("phase%d needs at least 2 LGR nodes", ip + 1));
+        run_compaction(h, p, 1, nullptr, nullptr, nullptr, true);
+        p.d_ddiag.reserve((size_t)N);
+        CK(cudaMemsetAsync(p.d_ddiag.p, 0, (size_t)N * sizeof(double), h->stream));
+        run_compaction(h, p, 1, nullptr, nullptr, p.d_ddiag.p, false);
+        const int ndoff = run_compaction(h, p, 0, nullptr, nullptr, nullptr, true);
+        p.d_doff_a.reserve((size_t)ndoff + 1); p.d_doff_b.reserve((size_t)ndoff + 1); p.d_doff_vals.reserve((size_t)ndoff + 1);
+        run_compaction(h, p, 0, p.d_doff_a.p, p.d_doff_b.p, p.d_doff_vals.p, false);
+        if (p.dep.empty()) p.dep.assign((size_t)(ns + np) * (ns + nc), 1); // probe not run: dense mask
+        build_hess_blocks(ns, nc, np, p.dep, p.pair_a, p.pair_b, p.hblk);
+        p.d_hblk.upload(p.hblk, h->stream);
+        p.d_pair_a.upload(p.pair_a, h->stream);
+        p.d_pair_b.upload(p.pair_b, h->stream);
+        PhaseShape& s = L.ph[ip];
+        s.N = N; s.ne = p.ne; s.ndoff = ndoff; s.nblkH = (int)p.pair_a.size();
+        T.doff_a[ip] = p.d_doff_a.p; T.doff_b[ip] = p.d_doff_b.p;
+        T.pair_a[ip] = p.d_pair_a.p; T.pair_b[ip] = p.d_pair_b.p;
+    }
+    for (int l = 0; l < Lp; ++l) {
+        L.lk[l].left = h->lk[l].left; L.lk[l].right = h->lk[l].right; L.lk[l].nl = (int)h->lk[l].lmin.size();
+    }
+    T.eent = h->d_eent.p;
+    if (!build_layout(L)) throw ApiError(LPB_ERR_INVALID, "problem too large for IPOPT's 32-bit Index");
+
+    // kernel-side description
+    pd.P = P; pd.Lp = Lp; pd.ns = ns; pd.nc = nc; pd.np = np;
+    pd.tol = h->tol; pd.analytic = h->first_derive == LPB_DERIVE_ANALYTIC ? 1 : 0;
+    pd.n = L.n; pd.m = L.m; pd.nnz_jac = (int)L.nnz_jac; pd.nnz_h = (int)L.nnz_h;
+    pd.total_nodes = L.total_nodes; pd.lin_con0 = L.lin_con0; pd.lin_val0 = L.lin_val0; pd.ctot = L.ctot;
+    for (int ip = 0; ip < P; ++ip) {
+        PhaseHost& p = h->ph[ip];
+        PhaseDev& d = pd.ph[ip];
+        d.N = L.ph[ip].N; d.K = p.tab.K; d.ne = p.ne;
+        d.node0 = L.node0[ip]; d.var0 = L.ph[ip].var0; d.con0 = L.ph[ip].con0;
+        d.ndoff = L.ph[ip].ndoff; d.nblkH = L.ph[ip].nblkH;
+        d.nl0 = L.nl0[ip]; d.ev0 = L.ev0[ip]; d.c0 = L.c0[ip]; d.hI0 = L.hI0[ip]; d.hE0 = L.hE0[ip];
+        d.tau = p.d_tau.p; d.w = p.d_w.p; d.ddiag = p.d_ddiag.p; d.node_interval = p.d_node_interval.p;
+        d.int_row0 = p.d_int_row0.p; d.int_n = p.d_int_n.p; d.int_d0 = p.d_int_d0.p; d.dblocks = p.d_dblocks.p;
+        d.doff_vals = p.d_doff_vals.p; d.hblk = p.d_hblk.p;
+    }
+    for (int l = 0; l < Lp; ++l) {
+        LinkDev& d = pd.lk[l];
+        d.left = L.lk[l].left; d.right = L.lk[l].right; d.nl = L.lk[l].nl;
+        d.con0 = L.lk[l].con0; d.lam0 = L.lam0[l]; d.val0 = L.lkv0[l]; d.h0 = L.hL0[l];
+    }
+    pd.eent = h->d_eent.p; pd.lent = h->d_lent.p;
+    pd.n_eent = (int)h->eent.size(); pd.n_lent = (int)h->lent.size();
+
+    // index maps on the GPU
+    h->d_jI.reserve((size_t)L.nnz_jac); h->d_jJ.reserve((size_t)L.nnz_jac);
+    h->d_hI.reserve((size_t)L.nnz_h); h->d_hJ.reserve((size_t)L.nnz_h);
+    k_jac_structure<<<(unsigned)((L.nnz_jac + 255) / 256), 256, 0, h->stream>>>(L, T, h->d_jI.p, h->d_jJ.p);
+    k_hess_structure<<<(unsigned)((L.nnz_h + 255) / 256), 256, 0, h->stream>>>(L, T, h->d_hI.p, h->d_hJ.p);
+    h->launches += 2;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    h->fresh = true;
+}
+
+static void need_fresh(lpb_handle* h)
+{
+    if (!h->fresh) refresh(h);
+}
+
+static void note_launches(lpb_handle* h, int rc)
+{
+    if (rc < 0) throw CudaError(std::string("kernel launch failed: ") + cudaGetErrorString((cudaError_t)(-(rc + 1000))));
+    h->launches += rc;
+}
+
+static void ensure_scratch(lpb_handle* h, int nbatch)
+{
+    h->d_scratch.reserve(h->vt->scratch_doubles(h->pd, nbatch));
+}
+
+// ---- C ABI ----------------------------------------------------------------------------------
+extern "C" {
+
+int lpb_num_functors(void)
+{
+    int n = 0;
+    functor_registry(&n);
+    return n;
+}
+
+const char* lpb_functor_name(int i)
+{
+    int n = 0;
+    const FunctorVTable* const* t = functor_registry(&n);
+    return (i >= 0 && i < n) ? t[i]->name : nullptr;
+}
+
+const char* lpb_last_error(const lpb_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int lpb_create(const lpb_problem_desc* desc, lpb_handle** out)
+{
+    if (!desc || !out) { g_create_error = "null argument"; return LPB_ERR_INVALID; }
+    *out = nullptr;
+    lpb_handle* h = nullptr;
+    try {
+        h = new lpb_handle();
+        int nf = 0;
+        const FunctorVTable* const* tab = functor_registry(&nf);
+        for (int i = 0; i < nf; ++i)
+            if (desc->functor && std::strcmp(desc->functor, tab[i]->name) == 0) h->vt = tab[i];
+        if (!h->vt) throw ApiError(LPB_ERR_UNKNOWN_FUNCTOR, fmt("unknown functor set '%s'", desc->functor ? desc->functor : "(null)"));
+        if (desc->nphases < 1 || desc->nphases > kMaxPhases) throw ApiError(LPB_ERR_INVALID, fmt("nphases must be 1..%d", kMaxPhases));
+        if (desc->nlinkpairs < 0 || desc->nlinkpairs > kMaxLinks) throw ApiError(LPB_ERR_INVALID, fmt("nlinkpairs must be 0..%d", kMaxLinks));
+        h->tol = desc->fd_tol > 0 ? desc->fd_tol : 1e-6; // "finite-difference-tol" default, LpOptDerive.hpp:29
+        h->first_derive = desc->first_derive;
+        if (h->first_derive == LPB_DERIVE_ANALYTIC && !h->vt->has_analytic)
+            throw ApiError(LPB_ERR_INVALID, "functor set has no analytic derivatives");
+        h->consts.assign((size_t)h->vt->consts_doubles, 0.0);
+        if (desc->consts)
+            for (int i = 0; i < desc->nconsts && i < h->vt->consts_doubles; ++i) h->consts[i] = desc->consts[i];
+        for (int ip = 0; ip < desc->nphases; ++ip) {
+            const lpb_phase_desc& d = desc->phases[ip];
+            if (d.nparameters != 0)
+                throw ApiError(LPB_ERR_UNSUPPORTED, "parameters (nq>0) are unsupported: the reference is self-inconsistent there (quirk Q3)");
+            if (d.nstates != h->vt->NS || d.ncontrols != h->vt->NC || d.npaths != h->vt->NPATH || d.nevents < 0 || d.nevents > h->vt->NE_MAX)
+                throw ApiError(LPB_ERR_INVALID, fmt("phase %d sizes do not match functor set %s", ip + 1, h->vt->name));
+            h->ph.emplace_back();
+            PhaseHost& p = h->ph.back();
+            p.ns = d.nstates; p.nc = d.ncontrols; p.nq = 0; p.np = d.npaths; p.ne = d.nevents;
+            copy_vec(p.smin0, d.state_min0, p.ns, "state_min0"); copy_vec(p.smin, d.state_min, p.ns, "state_min"); copy_vec(p.sminf, d.state_minf, p.ns, "state_minf");
+            copy_vec(p.smax0, d.state_max0, p.ns, "state_max0"); copy_vec(p.smax, d.state_max, p.ns, "state_max"); copy_vec(p.smaxf, d.state_maxf, p.ns, "state_maxf");
+            copy_vec(p.cmin, d.control_min, p.nc, "control_min"); copy_vec(p.cmax, d.control_max, p.nc, "control_max");
+            copy_vec(p.pmin, d.path_min, p.np, "path_min"); copy_vec(p.pmax, d.path_max, p.np, "path_max");
+            copy_vec(p.emin, d.event_min, p.ne, "event_min"); copy_vec(p.emax, d.event_max, p.ne, "event_max");
+            p.t0_min = d.t0_min; p.t0_max = d.t0_max; p.tf_min = d.tf_min; p.tf_max = d.tf_max;
+            p.has_duration = d.has_duration; p.dur_min = d.duration_min; p.dur_max = d.duration_max;
+            // bound consistency (LpBoundsChecker.cpp:56-58,:92-94,:145-147,:169-171,:300-303)
+            for (int j = 0; j < p.ns; ++j)
+                if (!(p.smin0[j] <= p.smax0[j] && p.smin[j] <= p.smax[j] && p.sminf[j] <= p.smaxf[j]))
+                    throw ApiError(LPB_ERR_INVALID, fmt("Bounds on State are Inconsistent (i.e. max < min) in Phase:%d", ip + 1));
+            for (int j = 0; j < p.nc; ++j)
+                if (!(p.cmin[j] <= p.cmax[j])) throw ApiError(LPB_ERR_INVALID, fmt("Bounds on Control are Inconsistent (i.e. max < min) in Phase:%d", ip + 1));
+            for (int j = 0; j < p.np; ++j)
+                if (!(p.pmin[j] <= p.pmax[j])) throw ApiError(LPB_ERR_INVALID, fmt("Bounds on path are Inconsistent (i.e. max < min) in Phase:%d", ip + 1));
+            for (int j = 0; j < p.ne; ++j)
+                if (!(p.emin[j] <= p.emax[j])) throw ApiError(LPB_ERR_INVALID, fmt("Bounds on event are Inconsistent (i.e. max < min) in Phase:%d", ip + 1));
+            if (p.has_duration && !(p.dur_min <= p.dur_max))
+                throw ApiError(LPB_ERR_INVALID, fmt("Bounds on duration are Inconsistent (i.e. max < min) in Phase:%d", ip + 1));
+            // default first mesh: [-1, 1] with 20 nodes (LpMeshRefiner.cpp:30-31,:50; quirk Q2)
+            p.mesh = {-1.0, 1.0};
+            p.nodes = {20};
+        }
+        int nl_common = -1;
+        for (int l = 0; l < desc->nlinkpairs; ++l) {
+            const lpb_link_desc& d = desc->links[l];
+            if (d.left_phase < 1 || d.left_phase > desc->nphases || d.right_phase < 1 || d.right_phase > desc->nphases)
+                throw ApiError(LPB_ERR_INVALID, fmt("linkage %d: phase out of range", l + 1));
+            if (d.nlinks < 1 || d.nlinks > h->vt->NL_MAX) throw ApiError(LPB_ERR_INVALID, fmt("linkage %d: nlinks must be 1..%d", l + 1, h->vt->NL_MAX));
+            if (nl_common >= 0 && nl_common != d.nlinks) throw ApiError(LPB_ERR_INVALID, "all link pairs must have the same number of links");
+            nl_common = d.nlinks;
+            h->lk.emplace_back();
+            LinkHost& k = h->lk.back();
+            k.left = d.left_phase - 1; k.right = d.right_phase - 1;
+            copy_vec(k.lmin, d.link_min, d.nlinks, "link_min"); copy_vec(k.lmax, d.link_max, d.nlinks, "link_max");
+            for (int j = 0; j < d.nlinks; ++j)
+                if (!(k.lmin[j] <= k.lmax[j])) throw ApiError(LPB_ERR_INVALID, fmt("Bounds on link are Inconsistent (i.e. max < min) in pair:%d", l + 1));
+        }
+        // device: no CPU fallback
+        int ndev = 0;
+        cudaError_t ce = cudaGetDeviceCount(&ndev);
+        if (ce != cudaSuccess || ndev < 1)
+            throw CudaError(std::string("no usable CUDA device (the transcription hot path has no CPU fallback): ") + cudaGetErrorString(ce));
+        int dev = 0;
+        CK(cudaGetDevice(&dev));
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, dev));
+        h->opts.sm_count = prop.multiProcessorCount;
+        h->opts.block = 128;
+        CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        h->own_stream = true;
+        build_entry_tables(h->vt->NS, h->eent, h->lent);
+        h->d_eent.upload(h->eent, h->stream);
+        h->d_lent.upload(h->lent, h->stream);
+        *out = h;
+        return LPB_OK;
+    } catch (const ApiError& e) {
+        g_create_error = e.what();
+        delete h;
+        return e.code;
+    } catch (const CudaError& e) {
+        g_create_error = e.what();
+        delete h;
+        return LPB_ERR_CUDA;
+    } catch (const std::exception& e) {
+        g_create_error = e.what();
+        delete h;
+        return LPB_ERR_INVALID;
+    }
+}
+
+int lpb_destroy(lpb_handle* h)
+{
+    if (!h) return LPB_ERR_INVALID;
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    delete h;
+    return LPB_OK;
+}
+
+int lpb_set_stream(lpb_handle* h, void* cuda_stream)
+{
+    LPB_API_BEGIN(h)
+    if (h->own_stream && h->stream) { CK(cudaStreamSynchronize(h->stream)); cudaStreamDestroy(h->stream); }
+    h->stream = (cudaStream_t)cuda_stream;
+    h->own_stream = false;
+    LPB_API_END(h)
+}
+
+int lpb_set_mesh(lpb_handle* h, int phase, int K, const double* meshpoints, const int* nodes_per_interval)
+{
+    LPB_API_BEGIN(h)
+    if (phase < 0 || phase >= (int)h->ph.size()) throw ApiError(LPB_ERR_INVALID, "phase out of range");
+    if (K < 1 || !meshpoints || !nodes_per_interval)
+        throw ApiError(LPB_ERR_INVALID, fmt("MeshRefinement need at least two meshPoints in phase%d", phase + 1));
+    if (meshpoints[0] != -1 || meshpoints[K] != 1) throw ApiError(LPB_ERR_INVALID, fmt("meshPoints must span -1 to +1 in phase%d", phase + 1));
+    for (int k = 0; k < K; ++k) {
+        if (nodes_per_interval[k] < 2) throw ApiError(LPB_ERR_INVALID, "nodes per interval must be >= 2");
+        if (!(meshpoints[k + 1] > meshpoints[k])) throw ApiError(LPB_ERR_INVALID, "meshPoints must be strictly increasing");
+    }
+    h->ph[phase].mesh.assign(meshpoints, meshpoints + K + 1);
+    h->ph[phase].nodes.assign(nodes_per_interval, nodes_per_interval + K);
+    h->fresh = false;
+    LPB_API_END(h)
+}
+
+int lpb_refresh(lpb_handle* h)
+{
+    LPB_API_BEGIN(h)
+    refresh(h);
+    LPB_API_END(h)
+}
+
+int lpb_get_nlp_info(lpb_handle* h, int* n, int* m, int* nnz_jac_g, int* nnz_h_lag)
+{
+    LPB_API_BEGIN(h)
+    need_fresh(h);
+    if (n) *n = h->pd.n;
+    if (m) *m = h->pd.m;
+    if (nnz_jac_g) *nnz_jac_g = h->pd.nnz_jac;
+    if (nnz_h_lag) *nnz_h_lag = h->pd.nnz_h;
+    LPB_API_END(h)
+}
+
+int lpb_get_bounds_info(lpb_handle* h, double* x_l, double* x_u, double* g_l, double* g_u)
+{
+    LPB_API_BEGIN(h)
+    need_fresh(h);
+    // LpBoundsChecker.cpp:51-185 (variables / constraints per phase), :226-253 (links), :265-346 (linear)
+    size_t iv = 0, ic = 0;
+    for (size_t ip = 0; ip < h->ph.size(); ++ip) {
+        const PhaseHost& p = h->ph[ip];
+        const int N = p.tab.N;
+        for (int j = 0; j < p.ns; ++j) {
+            if (x_l) { x_l[iv] = p.smin0[j]; x_u[iv] = p.smax0[j]; }
+            ++iv;
+            for (int k = 1; k < N; ++k) { if (x_l) { x_l[iv] = p.smin[j]; x_u[iv] = p.smax[j]; } ++iv; }
+            if (x_l) { x_l[iv] = p.sminf[j]; x_u[iv] = p.smaxf[j]; }
+            ++iv;
+        }
+        for (int j = 0; j < p.nc; ++j)
+            for (int k = 0; k < N; ++k) { if (x_l) { x_l[iv] = p.cmin[j]; x_u[iv] = p.cmax[j]; } ++iv; }
+        if (x_l) { x_l[iv] = p.t0_min; x_u[iv] = p.t0_max; x_l[iv + 1] = p.tf_min; x_u[iv + 1] = p.tf_max; }
+        iv += 2;
+        for (int j = 0; j < p.ns; ++j)
+            for (int k = 0; k < N; ++k) { if (g_l) { g_l[ic] = 0.0; g_u[ic] = 0.0; } ++ic; }
+        for (int j = 0; j < p.np; ++j)
+            for (int k = 0; k < N; ++k) { if (g_l) { g_l[ic] = p.pmin[j]; g_u[ic] = p.pmax[j]; } ++ic; }
+        for (int j = 0; j < p.ne; ++j) { if (g_l) { g_l[ic] = p.emin[j]; g_u[ic] = p.emax[j]; } ++ic; }
+    }
+    for (const LinkHost& k : h->lk)
+        for (size_t j = 0; j < k.lmin.size(); ++j) { if (g_l) { g_l[ic] = k.lmin[j]; g_u[ic] = k.lmax[j]; } ++ic; }
+    for (size_t ip = 0; ip < h->ph.size(); ++ip) {
+        const PhaseHost& p = h->ph[ip];
+        if (g_l) {
+            g_l[ic] = p.has_duration ? p.dur_min : 0.0;
+            g_u[ic] = p.has_duration ? p.dur_max : std::numeric_limits<double>::infinity();
+        }
+        ++ic;
+    }
+    for (size_t l = 0; l < h->lk.size(); ++l) { if (g_l) { g_l[ic] = 0.0; g_u[ic] = 0.0; } ++ic; }
+    if ((int)iv != h->pd.n || (int)ic != h->pd.m) throw ApiError(LPB_ERR_STATE, "internal: bounds layout mismatch");
+    LPB_API_END(h)
+}
+
+// ---- device-resident entry points -------------------------------------------------------------
+int lpb_eval_f_dev(lpb_handle* h, int nbatch, const double* d_x, double* d_obj)
+{
+    LPB_API_BEGIN(h)
+    need_fresh(h);
+    if (nbatch < 1) throw ApiError(LPB_ERR_INVALID, "nbatch must be >= 1");
+    ensure_scratch(h, nbatch);
+    note_launches(h, h->vt->objective(h->pd, h->consts.data(), h->stream, h->opts, nbatch, d_x, d_obj, h->d_scratch.p));
+    LPB_API_END(h)
+}
+
+int lpb_eval_grad_f_dev(lpb_handle* h, int nbatch, const double* d_x, double* d_grad)
+{
+    LPB_API_BEGIN(h)
+    need_fresh(h);
+    if (nbatch < 1) throw ApiError(LPB_ERR_INVALID, "nbatch must be >= 1");
+    ensure_scratch(h, nbatch);
+    note_launches(h, h->vt->gradient(h->pd, h->consts.data(), h->stream, h->opts, nbatch, d_x, d_grad, h->d_scratch.p));
+    LPB_API_END(h)
+}
+
+int lpb_eval_g_jac_dev(lpb_handle* h, int nbatch, const double* d_x, double* d_g, double* d_values)
+{
+    LPB_API_BEGIN(h)
+    need_fresh(h);
+    if (nbatch < 1) throw ApiError(LPB_ERR_INVALID, "nbatch must be >= 1");
+    if (!d_g && !d_values) return LPB_OK;
+    note_launches(h, h->vt->cons_jac(h->pd, h->consts.data(), h->stream, h->opts, nbatch, d_x, d_g, d_values));
+    LPB_API_END(h)
+}
+
+int lpb_eval_h_dev(lpb_handle* h, int nbatch, const double* d_x, const double* d_obj_factor, const double* d_lambda, double* d_values)
+{
+    LPB_API_BEGIN(h)
+    need_fresh(h);
+    if (nbatch < 1) throw ApiError(LPB_ERR_INVALID, "nbatch must be >= 1");
+    ensure_scratch(h, nbatch);
+    note_launches(h, h->vt->hessian(h->pd, h->consts.data(), h->stream, h->opts, nbatch, d_x, d_obj_factor, d_lambda, d_values, h->d_scratch.p));
+    LPB_API_END(h)
+}
+
+int lpb_structure_dev(lpb_handle* h, const int** d_jac_iRow, const int** d_jac_jCol, const int** d_h_iRow, const int** d_h_jCol)
+{
+    LPB_API_BEGIN(h)
+    need_fresh(h);
+    if (d_jac_iRow) *d_jac_iRow = h->d_jI.p;
+    if (d_jac_jCol) *d_jac_jCol = h->d_jJ.p;
+    if (d_h_iRow) *d_h_iRow = h->d_hI.p;
+    if (d_h_jCol) *d_h_jCol = h->d_hJ.p;
+    LPB_API_END(h)
+}
+
+// ---- host-pointer entry points (TNLP-style) ---------------------------------------------------
+static void h2d(lpb_handle* h, DevBuf<double>& buf, const double* src, size_t n)
+{
+    buf.reserve(n);
+    CK(cudaMemcpyAsync(buf.p, src, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+}
+static void d2h(lpb_handle* h, double* dst, const double* src, size_t n)
+{
+    CK(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+}
+
+int lpb_eval_f_batch(lpb_handle* h, int nbatch, const double* x, double* obj_values)
+{
+    LPB_API_BEGIN(h)
+    need_fresh(h);
+    if (nbatch < 1 || !x || !obj_values) throw ApiError(LPB_ERR_INVALID, "bad argument");
+    h2d(h, h->d_x, x, (size_t)nbatch * h->pd.n);
+    h->d_f.reserve((size_t)nbatch);
+    int rc = lpb_eval_f_dev(h, nbatch, h->d_x.p, h->d_f.p);
+    if (rc != LPB_OK) return rc;
+    d2h(h, obj_values, h->d_f.p, (size_t)nbatch);
+    CK(cudaStreamSynchronize(h->stream));
+    LPB_API_END(h)
+}
+
+int lpb_eval_grad_f_batch(lpb_handle* h, int nbatch, const double* x, double* grad_f)
+{
+    LPB_API_BEGIN(h)
+    need_fresh(h);
+    if (nbatch < 1 || !x || !grad_f) throw ApiError(LPB_ERR_INVALID, "bad argument");
+    h2d(h, h->d_x, x, (size_t)nbatch * h->pd.n);
+    h->d_grad.reserve((size_t)nbatch * h->pd.n);
+    int rc = lpb_eval_grad_f_dev(h, nbatch, h->d_x.p, h->d_grad.p);
+    if (rc != LPB_OK) return rc;
+    d2h(h, grad_f, h->d_grad.p, (size_t)nbatch * h->pd.n);
+    CK(cudaStreamSynchronize(h->stream));
+    LPB_API_END(h)
+}
+
+int lpb_eval_g_jac_batch(lpb_handle* h, int nbatch, const double* x, double* g, double* values)
+{
+    LPB_API_BEGIN(h)
+    need_fresh(h);
+    if (nbatch < 1 || !x) throw ApiError(LPB_ERR_INVALID, "bad argument");
+    h2d(h, h->d_x, x, (size_t)nbatch * h->pd.n);
+    if (g) h->d_g.reserve((size_t)nbatch * h->pd.m);
+    if (values) h->d_vals.reserve((size_t)nbatch * h->pd.nnz_jac);
+    int rc = lpb_eval_g_jac_dev(h, nbatch, h->d_x.p, g ? h->d_g.p : nullptr, values ? h->d_vals.p : nullptr);
+    if (rc != LPB_OK) return rc;
+    if (g) d2h(h, g, h->d_g.p, (size_t)nbatch * h->pd.m);
+    if (values) d2h(h, values, h->d_vals.p, (size_t)nbatch * h->pd.nnz_jac);
+    CK(cudaStreamSynchronize(h->stream));
+    LPB_API_END(h)
+}
+
+int lpb_eval_h_batch(lpb_handle* h, int nbatch, const double* x, const double* obj_factor, const double* lambda, double* values)
+{
+    LPB_API_BEGIN(h)
+    need_fresh(h);
+    if (nbatch < 1 || !x || !obj_factor || !lambda || !values) throw ApiError(LPB_ERR_INVALID, "bad argument");
+    h2d(h, h->d_x, x, (size_t)nbatch * h->pd.n);
+    h2d(h, h->d_lambda, lambda, (size_t)nbatch * h->pd.m);
+    h2d(h, h->d_sigma, obj_factor, (size_t)nbatch);
+    h->d_hvals.reserve((size_t)nbatch * h->pd.nnz_h);
+    int rc = lpb_eval_h_dev(h, nbatch, h->d_x.p, h->d_sigma.p, h->d_lambda.p, h->d_hvals.p);
+    if (rc != LPB_OK) return rc;
+    d2h(h, values, h->d_hvals.p, (size_t)nbatch * h->pd.nnz_h);
+    CK(cudaStreamSynchronize(h->stream));
+    LPB_API_END(h)
+}
+
+int lpb_eval_f(lpb_handle* h, const double* x, double* obj_value) { return lpb_eval_f_batch(h, 1, x, obj_value); }
+int lpb_eval_grad_f(lpb_handle* h, const double* x, double* grad_f) { return lpb_eval_grad_f_batch(h, 1, x, grad_f); }
+int lpb_eval_g(lpb_handle* h, const double* x, double* g) { return lpb_eval_g_jac_batch(h, 1, x, g, nullptr); }
+int lpb_eval_g_jac(lpb_handle* h, const double* x, double* g, double* values) { return lpb_eval_g_jac_batch(h, 1, x, g, values); }
+
+int lpb_eval_jac_g(lpb_handle* h, const double* x, int* iRow, int* jCol, double* values)
+{
+    if (values) return lpb_eval_g_jac_batch(h, 1, x, nullptr, values);
+    LPB_API_BEGIN(h)
+    need_fresh(h);
+    if (!iRow || !jCol) throw ApiError(LPB_ERR_INVALID, "iRow/jCol must be given when values == NULL");
+    CK(cudaMemcpyAsync(iRow, h->d_jI.p, (size_t)h->pd.nnz_jac * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(jCol, h->d_jJ.p, (size_t)h->pd.nnz_jac * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    LPB_API_END(h)
+}
+
+int lpb_eval_h(lpb_handle* h, const double* x, double obj_factor, const double* lambda, int* iRow, int* jCol, double* values)
+{
+    if (values) return lpb_eval_h_batch(h, 1, x, &obj_factor, lambda, values);
+    LPB_API_BEGIN(h)
+    need_fresh(h);
+    if (!iRow || !jCol) throw ApiError(LPB_ERR_INVALID, "iRow/jCol must be given when values == NULL");
+    CK(cudaMemcpyAsync(iRow, h->d_hI.p, (size_t)h->pd.nnz_h * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(jCol, h->d_hJ.p, (size_t)h->pd.nnz_h * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    LPB_API_END(h)
+}
+
+int lpb_probe_dependencies(lpb_handle* h, const double* x_guess, int* dep_out)
+{
+    LPB_API_BEGIN(h)
+    need_fresh(h);
+    if (!x_guess) throw ApiError(LPB_ERR_INVALID, "x_guess is null");
+    const int ns = h->vt->NS, nc = h->vt->NC, np = h->vt->NPATH;
+    const size_t per = (size_t)(ns + np) * (ns + nc);
+    h2d(h, h->d_x, x_guess, (size_t)h->pd.n);
+    h->d_dep.reserve(per * h->ph.size());
+    note_launches(h, h->vt->probe(h->pd, h->consts.data(), h->stream, h->d_x.p, h->d_dep.p));
+    std::vector<int> dep(per * h->ph.size());
+    CK(cudaMemcpyAsync(dep.data(), h->d_dep.p, dep.size() * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (size_t ip = 0; ip < h->ph.size(); ++ip) h->ph[ip].dep.assign(dep.begin() + ip * per, dep.begin() + (ip + 1) * per);
+    if (dep_out) std::memcpy(dep_out, dep.data(), dep.size() * sizeof(int));
+    refresh(h); // the Hessian pattern depends on the mask (LpHessian.cpp:2532-2536)
+    LPB_API_END(h)
+}
+
+int lpb_set_option_int(lpb_handle* h, const char* name, int value)
+{
+    LPB_API_BEGIN(h)
+    if (!name) throw ApiError(LPB_ERR_INVALID, "option name is null");
+    if (!std::strcmp(name, "colour_split")) h->opts.colour_split = value;
+    else if (!std::strcmp(name, "pair_split")) h->opts.pair_split = value;
+    else if (!std::strcmp(name, "block")) h->opts.block = value;
+    else throw ApiError(LPB_ERR_INVALID, std::string("unknown option ") + name);
+    LPB_API_END(h)
+}
+
+long long lpb_kernel_launch_count(const lpb_handle* h) { return h ? h->launches : 0; }
+
+} // extern "C"

@@ -1,0 +1,129 @@
+// lpb_tables.cpp -- see lpb_tables.hpp.
+#include "lpb_tables.hpp"
+#include <cmath>
+#include <map>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+
+namespace lpb {
+
+void lgr_points(int n, std::vector<double>& x, std::vector<double>& w)
+{
+    // Newton iteration on P_{n-1}(x) + P_n(x) with the Legendre three-term recurrence
+    // (RPMGenerator.cpp:253-291): start x_k = -cos(2 pi k/(2n-1)), x_0 stays at -1,
+    // iterate until max|dx| <= eps.
+    static std::map<int, std::pair<std::vector<double>, std::vector<double>>> cache;
+    static std::mutex mu;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = cache.find(n);
+        if (it != cache.end()) { x = it->second.first; w = it->second.second; return; }
+    }
+    const double pi = 3.14159265358979323846;
+    const double eps = 2.220446049250313e-16;
+    const int Nm = n - 1; // degree
+    x.assign(n, 0.0);
+    for (int k = 0; k < n; ++k) x[k] = -1 * std::cos((double)k * ((2 * pi) / (2 * Nm + 1)));
+    std::vector<double> P((size_t)n * (n + 1), 0.0); // P[i + n*deg]
+    std::vector<double> xold(n, 2.0);
+    for (;;) {
+        double mx = 0.0;
+        for (int i = 0; i < n; ++i) mx = std::fmax(mx, std::fabs(x[i] - xold[i]));
+        if (!(mx > eps)) break;
+        xold = x;
+        for (int i = 0; i < n; ++i) {
+            double* Pi = &P[i];
+            Pi[0] = 1.0;
+            Pi[n] = x[i];
+            for (int k = 1; k < n; ++k) Pi[(size_t)n * (k + 1)] = (x[i] * (2 * k + 1) * Pi[(size_t)n * k] - (Pi[(size_t)n * (k - 1)] * k)) / (k + 1);
+        }
+        for (int i = 1; i < n; ++i) {
+            double Pa = P[i + (size_t)n * (n - 1)], Pb = P[i + (size_t)n * n];
+            double step = (1.0 - xold[i]) / n;
+            step = step * (Pa + Pb);
+            x[i] = xold[i] - (step / (Pa - Pb));
+        }
+    }
+    w.assign(n, 0.0);
+    w[0] = 2.0 / (n * n);
+    for (int i = 1; i < n; ++i) {
+        double q = P[i + (size_t)n * Nm] * n;
+        w[i] = (1 - x[i]) / (q * q);
+    }
+    std::lock_guard<std::mutex> lk(mu);
+    cache[n] = std::make_pair(x, w);
+}
+
+// pairwise two-accumulator sum, the reduction Armadillo's sum() applies per column
+static double sum2(const double* s, int n)
+{
+    double a = 0.0, b = 0.0;
+    int i, j;
+    for (i = 0, j = 1; j < n; i += 2, j += 2) { a += s[i]; b += s[j]; }
+    if (i < n) a += s[i];
+    return a + b;
+}
+
+void colloc_block(const std::vector<double>& s, std::vector<double>& D)
+{
+    const int M = (int)s.size(), n = M - 1;
+    // Y(i,j) = (delta_ij + s_i) - s_j ; p_i = prod_j Y(i,j) ; G(i,j) = (1/p_i)/((1/p_j) Y(i,j))
+    std::vector<double> Y((size_t)M * M), p(M), G((size_t)M * M);
+    for (int j = 0; j < M; ++j)
+        for (int i = 0; i < M; ++i) Y[i + (size_t)j * M] = ((i == j ? 1.0 : 0.0) + s[i]) - s[j];
+    for (int i = 0; i < M; ++i) {
+        double acc = 1.0;
+        for (int j = 0; j < M; ++j) acc *= Y[i + (size_t)j * M];
+        p[i] = acc;
+    }
+    for (int j = 0; j < M; ++j)
+        for (int i = 0; i < M; ++i) G[i + (size_t)j * M] = (1 / p[i]) / ((1 / p[j]) * Y[i + (size_t)j * M]);
+    // diagonal from the column sums: G(j,j) = 1 - sum_i G(i,j)   (RPMGenerator.cpp:116-122)
+    for (int j = 0; j < M; ++j) G[j + (size_t)j * M] = 1 - sum2(&G[(size_t)j * M], M);
+    // D = -G^T with the last row dropped, column-major n x M
+    D.assign((size_t)n * M, 0.0);
+    for (int j = 0; j < M; ++j)
+        for (int i = 0; i < n; ++i) D[i + (size_t)j * n] = -G[j + (size_t)i * M];
+}
+
+void build_phase_tables(int K, const double* mesh, const int* nodes, PhaseTables& out)
+{
+    if (K < 1) throw std::runtime_error("MeshRefinement need at least two meshPoints");
+    if (mesh[0] != -1 || mesh[K] != 1) throw std::runtime_error("meshPoints must span -1 to +1");
+    out = PhaseTables();
+    out.K = K;
+    long long d0 = 0;
+    int row0 = 0;
+    for (int k = 0; k < K; ++k) {
+        const int n = nodes[k];
+        if (n < 2) throw std::runtime_error("nodes per interval must be >= 2");
+        std::vector<double> x, w;
+        lgr_points(n, x, w);
+        const double tspan = mesh[k + 1] - mesh[k];
+        std::vector<double> sall(n + 1);
+        for (int i = 0; i < n; ++i) {
+            double s = x[i] + 1; // (x+1)*tspan/2 + mesh_k   (RPMGenerator.cpp:67-69)
+            s *= tspan / 2.0;
+            s += mesh[k];
+            sall[i] = s;
+            out.tau.push_back(s);
+            double ws = w[i] / 2; // w/2*tspan                (:72-73)
+            ws *= tspan;
+            out.w.push_back(ws);
+            out.node_interval.push_back(k);
+        }
+        sall[n] = mesh[k + 1];
+        std::vector<double> D;
+        colloc_block(sall, D);
+        out.int_n.push_back(n);
+        out.int_row0.push_back(row0);
+        out.int_d0.push_back(d0);
+        out.dblocks.insert(out.dblocks.end(), D.begin(), D.end());
+        d0 += (long long)n * (n + 1);
+        row0 += n;
+    }
+    out.N = row0;
+}
+
+} // namespace lpb

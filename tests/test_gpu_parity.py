@@ -1,0 +1,145 @@
+"""GPU parity: the CUDA path through the C ABI vs the CPU oracle on the same seeded inputs.
+
+Bar (BASELINE.json north_star): integer triplets bit-exact; fp64 function and Jacobian values
+within 1e-12 relative of the reference restatement; Hessian (second differences divided by
+h^2 ~ 1e-12, noise-dominated) compared bit-for-bit where the arithmetic is identical and to
+1e-12 relative on the scale of the stencil noise floor otherwise (see rel_err).
+"""
+import numpy as np
+import pytest
+
+import cases
+from oracle_lib import Oracle
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-12
+
+
+def rel_err(a, b, scale=None):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    s = np.maximum(np.abs(b), 1.0) if scale is None else scale
+    d = np.abs(a - b) / s
+    return float(np.nanmax(d)) if d.size else 0.0
+
+
+@pytest.fixture(scope="module")
+def nlp_mod():
+    from lpopc_b200 import nlp
+    nlp.load_library()
+    return nlp
+
+
+@pytest.mark.parametrize("name", cases.CASES + ["launch/u5x4", "hypersensitive/u40x3", "orbit_raising/u200x10"])
+def test_parity_all_callbacks(nlp_mod, name):
+    op = cases.build(name)
+    o = Oracle(op)
+    g = nlp_mod.TranscribedNLP(op)
+    # sizes + integer triplets: bit-exact
+    assert g.get_nlp_info() == (o.n, o.m, o.nnz_jac, o.nnz_h)
+    gi, gj = g.eval_jac_g(values=False)
+    oi, oj = o.jac_structure()
+    assert np.array_equal(gi, oi) and np.array_equal(gj, oj)
+    gi, gj = g.eval_h(values=False)
+    oi, oj = o.h_structure()
+    assert np.array_equal(gi, oi) and np.array_equal(gj, oj)
+    for a, b in zip(g.get_bounds_info(), o.bounds()):
+        assert np.array_equal(a, b)
+    guess, x, sigma, lam = cases.inputs(op, o, 7)
+    for xv in (guess, x):
+        assert abs(g.eval_f(xv) - o.eval_f(xv)) <= RTOL * max(1.0, abs(o.eval_f(xv)))
+        assert rel_err(g.eval_grad_f(xv), o.eval_grad_f(xv)) <= RTOL
+        assert rel_err(g.eval_g(xv), o.eval_g(xv)) <= RTOL
+        assert rel_err(g.eval_jac_g(xv), o.eval_jac_g(xv)) <= RTOL
+        gg, gv = g.eval_g_jac(xv)
+        assert np.array_equal(gg, g.eval_g(xv)) and np.array_equal(gv, g.eval_jac_g(xv))
+    # Hessian: identical arithmetic -> expect (near) bit equality; tolerance on the noise scale
+    hv_g, hv_o = g.eval_h(x, sigma, lam), o.eval_h(x, sigma, lam)
+    scale = np.maximum(np.abs(hv_o), 1.0)
+    assert rel_err(hv_g, hv_o, scale) <= 1e-9, "Hessian stencil mismatch"
+    frac_exact = float(np.mean(hv_g == hv_o))
+    assert frac_exact > 0.9, frac_exact
+
+
+def test_fd_jacobian_is_bit_exact_for_polynomial_functor(nlp_mod):
+    """Bryson-Denham uses + * only: host and device must agree to the last bit."""
+    op = cases.build("bryson_denham/ragged")
+    o, g = Oracle(op), nlp_mod.TranscribedNLP(op)
+    _, x, sigma, lam = cases.inputs(op, o, 3)
+    assert np.array_equal(g.eval_g(x), o.eval_g(x))
+    assert np.array_equal(g.eval_jac_g(x), o.eval_jac_g(x))
+    assert np.array_equal(g.eval_grad_f(x), o.eval_grad_f(x))
+    assert np.array_equal(g.eval_h(x, sigma, lam), o.eval_h(x, sigma, lam))
+
+
+def test_dependency_probe_and_sparse_hessian(nlp_mod):
+    op = cases.build("launch")
+    o, g = Oracle(op), nlp_mod.TranscribedNLP(op)
+    guess, x, sigma, lam = cases.inputs(op, o, 5)
+    dep_o, dep_g = o.probe_dependencies(guess), g.probe_dependencies(guess)
+    assert np.array_equal(dep_o, dep_g)
+    assert g.get_nlp_info() == (o.n, o.m, o.nnz_jac, o.nnz_h)
+    gi, gj = g.eval_h(values=False)
+    oi, oj = o.h_structure()
+    assert np.array_equal(gi, oi) and np.array_equal(gj, oj)
+    hv_g, hv_o = g.eval_h(x, sigma, lam), o.eval_h(x, sigma, lam)
+    assert rel_err(hv_g, hv_o) <= 1e-9
+
+
+def test_mesh_refresh_rebuilds_index_maps(nlp_mod):
+    """Adaptive refinement = new n, m, nnz, new index maps (north_star item 3)."""
+    op = cases.build("bryson_denham")
+    o, g = Oracle(op), nlp_mod.TranscribedNLP(op)
+    for seed, K in ((1, 2), (2, 5), (3, 9)):
+        cases.ragged_mesh(op.phases[0], seed, K, 3, 12)
+        o.set_mesh(0, op.phases[0].meshpoints, op.phases[0].nodesperinterval); o.refresh()
+        g.set_mesh(0, op.phases[0].meshpoints, op.phases[0].nodesperinterval); g.refresh()
+        assert g.get_nlp_info() == (o.n, o.m, o.nnz_jac, o.nnz_h)
+        for a, b in zip(g.eval_jac_g(values=False), o.jac_structure()):
+            assert np.array_equal(a, b)
+        for a, b in zip(g.eval_h(values=False), o.h_structure()):
+            assert np.array_equal(a, b)
+        _, x, _, _ = cases.inputs(op, o, seed)
+        assert rel_err(g.eval_jac_g(x), o.eval_jac_g(x)) <= RTOL
+
+
+def test_batched_instances_match_single(nlp_mod):
+    op = cases.build("quadrotor")
+    o, g = Oracle(op), nlp_mod.TranscribedNLP(op)
+    rng = np.random.Generator(np.random.PCG64(5))
+    guess = op.guess(cases.lgr_points_of(o))
+    nb = 37
+    X = guess[None, :] + 0.05 * rng.uniform(-1, 1, (nb, guess.size))
+    G, V = g.eval_g_jac_batch(X)
+    F = g.eval_f_batch(X)
+    GR = g.eval_grad_f_batch(X)
+    lam = rng.uniform(-1, 1, (nb, o.m))
+    sg = rng.uniform(0.5, 1.5, nb)
+    H = g.eval_h_batch(X, sg, lam)
+    og, ov = o.eval_g_jac_batch(X, nthreads=4)
+    assert rel_err(G, og) <= RTOL and rel_err(V, ov) <= RTOL
+    for b in (0, 17, nb - 1):
+        assert abs(F[b] - o.eval_f(X[b])) <= RTOL * max(1.0, abs(F[b]))
+        assert rel_err(GR[b], o.eval_grad_f(X[b])) <= RTOL
+        assert rel_err(H[b], o.eval_h(X[b], sg[b], lam[b])) <= 1e-9
+        assert np.array_equal(G[b], g.eval_g(X[b])) and np.array_equal(V[b], g.eval_jac_g(X[b]))
+
+
+def test_error_behaviour(nlp_mod):
+    from lpopc_b200 import examples
+    op = examples.hypersensitive()
+    op.phases[0].parameternum = 1
+    with pytest.raises(nlp_mod.LpopcError) as e:
+        nlp_mod.TranscribedNLP(op)
+    assert e.value.code == -2  # LPB_ERR_UNSUPPORTED (quirk Q3)
+    op = examples.hypersensitive()
+    op.phases[0].set_mesh([-1.0, 0.9], [4])
+    with pytest.raises(nlp_mod.LpopcError, match="span -1 to \\+1"):
+        nlp_mod.TranscribedNLP(op)
+    op = examples.bryson_denham()
+    op.functor = "nope"
+    with pytest.raises(nlp_mod.LpopcError) as e:
+        nlp_mod.TranscribedNLP(op)
+    assert e.value.code == -5
