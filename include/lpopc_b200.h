@@ -142,6 +142,10 @@ int lpb_structure_dev(lpb_handle* h, const int** d_jac_iRow, const int** d_jac_j
 /* Tuning / introspection (not part of the reference boundary). */
 int lpb_set_option_int(lpb_handle* h, const char* name, int value);
 long long lpb_kernel_launch_count(const lpb_handle* h); /* kernels launched so far */
+/* With option "time_kernels" = 1 every evaluation brackets its dominant node kernel
+ * ("cons_jac": k_cons_jac, "hess_nodes": k_hess_nodes) with CUDA events on the handle's
+ * stream; this returns and resets the accumulated device time and launch count. */
+int lpb_kernel_time(lpb_handle* h, const char* kernel, double* total_ms, int* count);
 int lpb_num_functors(void);
 const char* lpb_functor_name(int i);
 

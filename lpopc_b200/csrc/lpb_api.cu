@@ -260,6 +260,9 @@ struct lpb_handle {
     bool own_stream = false;
     long long launches = 0;
     std::string err;
+    // live kernel timing (option "time_kernels"): one event pair per timed launch
+    bool time_kernels = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed_cons, timed_hess;
     // structure
     DevBuf<int> d_jI, d_jJ, d_hI, d_hJ;
     DevBuf<HessEntry> d_eent, d_lent;
@@ -270,6 +273,8 @@ struct lpb_handle {
     lpb_handle() { std::memset(&pd, 0, sizeof pd); std::memset(&lay, 0, sizeof lay); std::memset(&ltab, 0, sizeof ltab); std::memset(&opts, 0, sizeof opts); }
     ~lpb_handle()
     {
+        for (auto* v : {&timed_cons, &timed_hess})
+            for (auto& pr : *v) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
         if (own_stream && stream) cudaStreamDestroy(stream);
     }
 };
@@ -425,6 +430,19 @@ static void note_launches(lpb_handle* h, int rc)
 {
     if (rc < 0) throw CudaError(std::string("kernel launch failed: ") + cudaGetErrorString((cudaError_t)(-(rc + 1000))));
     h->launches += rc;
+}
+
+// LaunchOpts of one call; in timing mode a fresh event pair brackets the dominant node kernel
+static LaunchOpts call_opts(lpb_handle* h, std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& sink)
+{
+    LaunchOpts o = h->opts;
+    o.ev_begin = o.ev_end = nullptr;
+    if (h->time_kernels) {
+        CK(cudaEventCreate(&o.ev_begin));
+        CK(cudaEventCreate(&o.ev_end));
+        sink.emplace_back(o.ev_begin, o.ev_end);
+    }
+    return o;
 }
 
 static void ensure_scratch(lpb_handle* h, int nbatch)
@@ -672,7 +690,8 @@ int lpb_eval_g_jac_dev(lpb_handle* h, int nbatch, const double* d_x, double* d_g
     need_fresh(h);
     if (nbatch < 1) throw ApiError(LPB_ERR_INVALID, "nbatch must be >= 1");
     if (!d_g && !d_values) return LPB_OK;
-    note_launches(h, h->vt->cons_jac(h->pd, h->consts.data(), h->stream, h->opts, nbatch, d_x, d_g, d_values));
+    const LaunchOpts o = d_values ? call_opts(h, h->timed_cons) : h->opts;
+    note_launches(h, h->vt->cons_jac(h->pd, h->consts.data(), h->stream, o, nbatch, d_x, d_g, d_values));
     LPB_API_END(h)
 }
 
@@ -682,7 +701,8 @@ int lpb_eval_h_dev(lpb_handle* h, int nbatch, const double* d_x, const double* d
     need_fresh(h);
     if (nbatch < 1) throw ApiError(LPB_ERR_INVALID, "nbatch must be >= 1");
     ensure_scratch(h, nbatch);
-    note_launches(h, h->vt->hessian(h->pd, h->consts.data(), h->stream, h->opts, nbatch, d_x, d_obj_factor, d_lambda, d_values, h->d_scratch.p));
+    const LaunchOpts o = call_opts(h, h->timed_hess);
+    note_launches(h, h->vt->hessian(h->pd, h->consts.data(), h->stream, o, nbatch, d_x, d_obj_factor, d_lambda, d_values, h->d_scratch.p));
     LPB_API_END(h)
 }
 
@@ -823,10 +843,34 @@ int lpb_set_option_int(lpb_handle* h, const char* name, int value)
     if (!std::strcmp(name, "colour_split")) h->opts.colour_split = value;
     else if (!std::strcmp(name, "pair_split")) h->opts.pair_split = value;
     else if (!std::strcmp(name, "block")) h->opts.block = value;
+    else if (!std::strcmp(name, "time_kernels")) h->time_kernels = value != 0;
     else throw ApiError(LPB_ERR_INVALID, std::string("unknown option ") + name);
     LPB_API_END(h)
 }
 
 long long lpb_kernel_launch_count(const lpb_handle* h) { return h ? h->launches : 0; }
+
+int lpb_kernel_time(lpb_handle* h, const char* kernel, double* total_ms, int* count)
+{
+    LPB_API_BEGIN(h)
+    if (!kernel) throw ApiError(LPB_ERR_INVALID, "kernel name is null");
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>>* v = nullptr;
+    if (!std::strcmp(kernel, "cons_jac")) v = &h->timed_cons;
+    else if (!std::strcmp(kernel, "hess_nodes")) v = &h->timed_hess;
+    else throw ApiError(LPB_ERR_INVALID, std::string("unknown kernel ") + kernel);
+    CK(cudaStreamSynchronize(h->stream));
+    double ms = 0.0;
+    for (auto& pr : *v) {
+        float t = 0.f;
+        CK(cudaEventElapsedTime(&t, pr.first, pr.second));
+        ms += t;
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    if (total_ms) *total_ms = ms;
+    if (count) *count = (int)v->size();
+    v->clear();
+    LPB_API_END(h)
+}
 
 } // extern "C"

@@ -76,6 +76,9 @@ struct LaunchOpts {
     int colour_split; // colour chunks (gridDim.y) of the Jacobian kernel; 0 = auto
     int pair_split;   // pair chunks of the Hessian kernel; 0 = auto
     int sm_count;
+    // optional CUDA events recorded on the launch stream right before / after the dominant
+    // node kernel (bench.py's live roofline measurement); null = no timing
+    cudaEvent_t ev_begin, ev_end;
 };
 
 // Dispatch table of one functor set (filled by LPB_DEFINE_FUNCTOR in lpb_kernels.cuh).

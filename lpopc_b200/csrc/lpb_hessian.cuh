@@ -374,7 +374,9 @@ int launch_hessian(const ProblemDev& pd, const void* consts, cudaStream_t st, co
     }
     if (split < 1) split = 1;
     if (split > D::NCOL) split = D::NCOL;
+    if (o.ev_begin) cudaEventRecord(o.ev_begin, st);
     k_hess_nodes<P><<<dim3(gx, split), block, 0, st>>>(pd, C, nbatch, x, sigma, lambda, vals, scratch);
+    if (o.ev_end) cudaEventRecord(o.ev_end, st);
     k_hess_endpoint<P><<<dim3(pd.P + pd.Lp, nbatch), 128, 0, st>>>(pd, C, nbatch, x, sigma, lambda, vals, scratch,
                                                                   pd.eent, pd.n_eent, pd.lent, pd.n_lent);
     cudaError_t e = cudaGetLastError();

@@ -52,6 +52,7 @@ SIGNATURES = {
     "lpb_structure_dev": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
     "lpb_set_option_int": (C.c_int, [_vp, C.c_char_p, C.c_int]),
     "lpb_kernel_launch_count": (C.c_longlong, [_vp]),
+    "lpb_kernel_time": (C.c_int, [_vp, C.c_char_p, _dp, _ip]),
     "lpb_num_functors": (C.c_int, []),
     "lpb_functor_name": (C.c_char_p, [C.c_int]),
 }
@@ -142,6 +143,12 @@ class TranscribedNLP:
     @property
     def kernel_launches(self):
         return int(self.lib.lpb_kernel_launch_count(self.h))
+
+    def kernel_time(self, kernel):
+        """(total device ms, launches) of the named node kernel since the last call (option time_kernels)."""
+        ms, cnt = C.c_double(), C.c_int()
+        self._ck(self.lib.lpb_kernel_time(self.h, kernel.encode(), C.byref(ms), C.byref(cnt)))
+        return ms.value, cnt.value
 
     # -- TNLP-shaped interface (LpopcIpopt.cpp:11-218) --
     def get_nlp_info(self):
