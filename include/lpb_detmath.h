@@ -70,11 +70,11 @@ LPB_HD double lpb_det_exp(double x)
     const double P3 = 6.61375632143793436117e-05;
     const double P4 = -1.65339022054652515390e-06;
     const double P5 = 4.13813679705723846039e-08;
-    if (x != x) return x;
-    if (x > 709.782712893384) return lpb_from_bits(0x7ff0000000000000LL);
-    if (x < -745.2) return 0.0;
-    double kd = floor(x * invln2 + 0.5);
-    double hi = x - kd * ln2HI;
+    const bool isnan_ = x != x;
+    const bool big = x > 709.782712893384, small = x < -745.2;
+    const double xr = (isnan_ || big || small) ? 0.0 : x;
+    double kd = floor(xr * invln2 + 0.5);
+    double hi = xr - kd * ln2HI;
     double lo = kd * ln2LO;
     double r = hi - lo;
     double t = r * r;
@@ -83,7 +83,10 @@ LPB_HD double lpb_det_exp(double x)
     long long k = (long long)kd;
     long long k1 = k / 2;
     long long k2 = k - k1;
-    return (y * lpb_pow2i(k1)) * lpb_pow2i(k2);
+    double v = (y * lpb_pow2i(k1)) * lpb_pow2i(k2);
+    v = small ? 0.0 : v;
+    v = big ? lpb_from_bits(0x7ff0000000000000LL) : v;
+    return isnan_ ? x : v;
 }
 
 /* ---- tanh --------------------------------------------------------------- */
@@ -169,26 +172,31 @@ LPB_HD double lpb_reduce_pio2(double x, long long* quadrant)
     return r;
 }
 
+/* sin/cos are straight-line code (selects, no branches): a perturbed dae() evaluation
+ * whose angle argument is unchanged is then a literal common subexpression of the base
+ * evaluation, which the compile-time colour unrolling of the Jacobian kernel relies on. */
 LPB_HD double lpb_det_sin(double x)
 {
-    if (!(fabs(x) < 1.0e6)) return lpb_det_nan(x);
+    const bool ok = fabs(x) < 1.0e6; /* false for NaN */
     long long q;
-    double r = lpb_reduce_pio2(x, &q);
+    double r = lpb_reduce_pio2(ok ? x : 0.0, &q);
     double s = lpb_ksin(r);
     double c = lpb_kcos(r);
     double v = (q & 1LL) ? c : s;
-    return (q & 2LL) ? -v : v;
+    v = (q & 2LL) ? -v : v;
+    return ok ? v : lpb_from_bits(0x7ff8000000000000LL);
 }
 
 LPB_HD double lpb_det_cos(double x)
 {
-    if (!(fabs(x) < 1.0e6)) return lpb_det_nan(x);
+    const bool ok = fabs(x) < 1.0e6;
     long long q;
-    double r = lpb_reduce_pio2(x, &q);
+    double r = lpb_reduce_pio2(ok ? x : 0.0, &q);
     double s = lpb_ksin(r);
     double c = lpb_kcos(r);
     double v = (q & 1LL) ? s : c;
-    return (((q + 1LL) & 2LL) != 0LL) ? -v : v;
+    v = (((q + 1LL) & 2LL) != 0LL) ? -v : v;
+    return ok ? v : lpb_from_bits(0x7ff8000000000000LL);
 }
 
 /* ---- acos --------------------------------------------------------------- */

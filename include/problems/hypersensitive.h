@@ -9,6 +9,7 @@
 struct LpbHypersensitive {
     static constexpr int NS = 1, NC = 1, NPATH = 0, NE_MAX = 0, NL_MAX = 0;
     static constexpr bool HAS_ANALYTIC = true;
+    static constexpr bool UNROLL_COLOURS = true; /* compile-time colour unrolling of the FD Jacobian kernel */
     struct Consts { double unused; };
     static const char* name() { return "hypersensitive"; }
 

@@ -193,29 +193,33 @@ k_compact_scatter(const __grid_constant__ CompactDev c, const int* __restrict__ 
         }
 }
 
-// constant Jacobian segment: Doffdiag values repeated per state (LpNLPWrapper.cpp:715-718);
-// one thread per output value, streaming stores
+// constant Jacobian segment: Doffdiag values repeated once per state (LpNLPWrapper.cpp:715-718).
+// grid = (Doffdiag tiles of the phase, phase, instance): a thread loads one Doffdiag value and
+// streams it to its slot in each of the ns state copies -- no index arithmetic beyond adds,
+// every store a coalesced 256-byte run per warp.
 __global__ void __launch_bounds__(256)
-k_fill_const(const __grid_constant__ ProblemDev pd, int nbatch, double* __restrict__ vals)
+k_fill_const(const __grid_constant__ ProblemDev pd, double* __restrict__ vals)
 {
-    const long long per = pd.ctot;
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= per * nbatch) return;
-    const int b = (int)(gid / per);
-    const long long e = gid - (long long)b * per;
-    int p = 0;
-    while (p + 1 < pd.P && e >= pd.ph[p + 1].c0 - pd.ph[0].c0) ++p;
-    const long long loc = e - (pd.ph[p].c0 - pd.ph[0].c0);
-    const int idx = (int)(loc % pd.ph[p].ndoff);
-    __stcs(vals + (size_t)b * pd.nnz_jac + pd.ph[0].c0 + e, pd.ph[p].doff_vals[idx]);
+    const PhaseDev& ph = pd.ph[blockIdx.y];
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= ph.ndoff) return;
+    const double v = ph.doff_vals[idx];
+    double* __restrict__ out = vals + (size_t)blockIdx.z * pd.nnz_jac + ph.c0 + idx;
+    for (int i = 0; i < pd.ns; ++i) __stcs(out + (size_t)i * ph.ndoff, v);
 }
 
 int launch_fill_const(const ProblemDev& pd, cudaStream_t st, int nbatch, double* vals)
 {
-    const long long tot = pd.ctot * nbatch;
-    if (tot <= 0) return 0;
-    k_fill_const<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(pd, nbatch, vals);
-    return 1;
+    if (pd.ctot <= 0) return 0;
+    int maxd = 0;
+    for (int p = 0; p < pd.P; ++p) maxd = pd.ph[p].ndoff > maxd ? pd.ph[p].ndoff : maxd;
+    int launches = 0;
+    for (int b0 = 0; b0 < nbatch; b0 += 65535) { // gridDim.z limit
+        const int nb = nbatch - b0 < 65535 ? nbatch - b0 : 65535;
+        k_fill_const<<<dim3((unsigned)((maxd + 255) / 256), pd.P, nb), 256, 0, st>>>(pd, vals + (size_t)b0 * pd.nnz_jac);
+        ++launches;
+    }
+    return launches;
 }
 
 } // namespace lpb
@@ -548,6 +552,7 @@ int lpb_create(const lpb_problem_desc* desc, lpb_handle** out)
         CK(cudaGetDeviceProperties(&prop, dev));
         h->opts.sm_count = prop.multiProcessorCount;
         h->opts.block = 128;
+        h->opts.unroll_colours = -1;
         CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         h->own_stream = true;
         build_entry_tables(h->vt->NS, h->eent, h->lent);
@@ -843,6 +848,7 @@ int lpb_set_option_int(lpb_handle* h, const char* name, int value)
     if (!std::strcmp(name, "colour_split")) h->opts.colour_split = value;
     else if (!std::strcmp(name, "pair_split")) h->opts.pair_split = value;
     else if (!std::strcmp(name, "block")) h->opts.block = value;
+    else if (!std::strcmp(name, "unroll_colours")) h->opts.unroll_colours = value;
     else if (!std::strcmp(name, "time_kernels")) h->time_kernels = value != 0;
     else throw ApiError(LPB_ERR_INVALID, std::string("unknown option ") + name);
     LPB_API_END(h)
