@@ -146,6 +146,9 @@ long long lpb_kernel_launch_count(const lpb_handle* h); /* kernels launched so f
  * ("cons_jac": k_cons_jac, "hess_nodes": k_hess_nodes) with CUDA events on the handle's
  * stream; this returns and resets the accumulated device time and launch count. */
 int lpb_kernel_time(lpb_handle* h, const char* kernel, double* total_ms, int* count);
+/* Device self-test: n pseudo-random (numerator, divisor) pairs through the shared-reciprocal
+ * forward-difference quotient of the Jacobian kernels vs IEEE division; *mismatches must be 0. */
+int lpb_selftest_fd_division(long long n, unsigned long long seed, long long* mismatches);
 int lpb_num_functors(void);
 const char* lpb_functor_name(int i);
 

@@ -12,6 +12,7 @@
 #include "lpb_device.hpp"
 #include "lpb_structure.hpp"
 #include "lpb_tables.hpp"
+#include "lpb_kernels.cuh"
 
 #include <cmath>
 #include <cstdarg>
@@ -220,6 +221,44 @@ int launch_fill_const(const ProblemDev& pd, cudaStream_t st, int nbatch, double*
         ++launches;
     }
     return launches;
+}
+
+// self-test of FdDiv (lpb_kernels.cuh): pseudo-random operand pairs, shared-reciprocal quotient
+// vs the compiler's IEEE division, compared bit for bit
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long& s)
+{
+    unsigned long long z = (s += 0x9e3779b97f4a7c15ULL);
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+    return z ^ (z >> 31);
+}
+
+__global__ void __launch_bounds__(256)
+k_selftest_fd_division(long long n, unsigned long long seed, unsigned long long* __restrict__ mismatches)
+{
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long bad = 0;
+    for (long long i = gid; i < n; i += (long long)gridDim.x * blockDim.x) {
+        unsigned long long s = seed + 0x632be59bd9b4e019ULL * (unsigned long long)i;
+        const unsigned long long a = splitmix64(s), b = splitmix64(s), c = splitmix64(s);
+        // divisor: positive; 3 of 4 in the working range of h = tol*(1+|v|), the rest any exponent
+        // (zero, denormal, inf and NaN included)
+        double h;
+        if ((c & 3) != 0) h = __longlong_as_double((long long)(((1023ULL - 40 + (c >> 2) % 60) << 52) | (a >> 12)));
+        else h = __longlong_as_double((long long)(a >> 1));
+        // numerator: any bit pattern, or a value close to the divisor's scale
+        double d;
+        if ((c >> 8) & 1) d = __longlong_as_double((long long)b);
+        else d = __longlong_as_double((long long)((b & 0x800fffffffffffffULL) | ((1023ULL - 60 + (c >> 16) % 90) << 52)));
+        const FdDiv dv(h);
+        const double q = dv.quot(d, 0.0); // d - 0.0 == d exactly
+        const double ref = d / h;
+        bool same = __double_as_longlong(q) == __double_as_longlong(ref);
+        if (!same && q != q && ref != ref) same = true; // any NaN equals any NaN
+        if (!same && d == 0.0 && !(h > 0.0)) same = true; // documented domain: h > 0 (or NaN)
+        bad += same ? 0 : 1;
+    }
+    if (bad) atomicAdd(mismatches, bad);
 }
 
 } // namespace lpb
@@ -852,6 +891,21 @@ int lpb_set_option_int(lpb_handle* h, const char* name, int value)
     else if (!std::strcmp(name, "time_kernels")) h->time_kernels = value != 0;
     else throw ApiError(LPB_ERR_INVALID, std::string("unknown option ") + name);
     LPB_API_END(h)
+}
+
+int lpb_selftest_fd_division(long long n, unsigned long long seed, long long* mismatches)
+{
+    if (!mismatches || n < 1) return LPB_ERR_INVALID;
+    unsigned long long* d = nullptr;
+    if (cudaMalloc((void**)&d, sizeof *d) != cudaSuccess) return LPB_ERR_CUDA;
+    cudaMemset(d, 0, sizeof *d);
+    k_selftest_fd_division<<<148 * 8, 256>>>(n, seed, d);
+    unsigned long long out = 0;
+    const cudaError_t e = cudaMemcpy(&out, d, sizeof out, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return LPB_ERR_CUDA;
+    *mismatches = (long long)out;
+    return LPB_OK;
 }
 
 long long lpb_kernel_launch_count(const lpb_handle* h) { return h ? h->launches : 0; }

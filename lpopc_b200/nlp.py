@@ -53,6 +53,7 @@ SIGNATURES = {
     "lpb_set_option_int": (C.c_int, [_vp, C.c_char_p, C.c_int]),
     "lpb_kernel_launch_count": (C.c_longlong, [_vp]),
     "lpb_kernel_time": (C.c_int, [_vp, C.c_char_p, _dp, _ip]),
+    "lpb_selftest_fd_division": (C.c_int, [C.c_longlong, C.c_ulonglong, C.POINTER(C.c_longlong)]),
     "lpb_num_functors": (C.c_int, []),
     "lpb_functor_name": (C.c_char_p, [C.c_int]),
 }
@@ -85,6 +86,15 @@ def _i(a):
 
 def _f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def selftest_fd_division(n, seed=1):
+    """Mismatches between the kernels' shared-reciprocal FD quotient and IEEE division over n random pairs."""
+    bad = C.c_longlong(-1)
+    rc = load_library().lpb_selftest_fd_division(int(n), int(seed), C.byref(bad))
+    if rc != LPB_OK:
+        raise RuntimeError("lpb_selftest_fd_division failed: %d" % rc)
+    return bad.value
 
 
 class LpopcError(RuntimeError):

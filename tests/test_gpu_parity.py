@@ -143,3 +143,10 @@ def test_error_behaviour(nlp_mod):
     with pytest.raises(nlp_mod.LpopcError) as e:
         nlp_mod.TranscribedNLP(op)
     assert e.value.code == -5
+
+
+@pytest.mark.gpu
+def test_fd_division_is_ieee(nlp_mod):
+    """The Jacobian kernels divide by the per-colour step h through one shared reciprocal
+    (FdDiv, lpb_kernels.cuh); every quotient must equal IEEE d / h bit for bit."""
+    assert nlp_mod.selftest_fd_division(1 << 28, seed=12345) == 0
