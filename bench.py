@@ -34,6 +34,9 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 INSTANCES_PER_GPU = 4096
 MESH_INTERVALS, MESH_NODES = 8, 8
 NBUF = 4  # rotating input sets so that x is not served from L2 between steps
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_cons_jac launch of this workload from the
+# committed `ncu --set full` capture (profiles/r01_cons_jac_full.txt); None until captured
+NCU_TRAFFIC_BYTES = None
 
 
 def quadrotor_problem():
@@ -332,8 +335,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": "nnz/s", "h2d_bytes_per_step": 8 * nb * n, "d2h_bytes_per_step": 8 * nb * (m + nnz),
                     "steps": e2e_steps, "ms_per_step": 1e3 * float(te.item()) / e2e_steps, "host_buffers": "pinned"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_cons_jac<LpbQuadrotor,true,true>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "bytes_per_launch": kbytes, "avg_launch_ms": kavg_ms,
+            "roofline": {"bound": "hbm", "kernel": "k_cons_jac<LpbQuadrotor,WANT_G=1,WANT_JAC=1,UNROLL=1>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES, "bytes_per_launch": kbytes, "avg_launch_ms": kavg_ms,
                          "launches_timed": kern_cnt, "peak_source": peak_src,
                          "step_bytes": 8 * nb * (n + m + nnz), "step_frac": 8 * nb * (n + m + nnz) / (ms / args.steps * 1e-3) / 1e9 / peak},
             "cpu_baseline": {"value": cpu_rate, "unit": "nnz/s", "cores": threads, "kind": "port",
