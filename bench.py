@@ -121,20 +121,75 @@ class ClockSampler:
                 "samples": len(sm), "source": "NVML polled every 2 ms inside the timed region"}
 
 
+REF_LIB = os.path.join(ROOT, "oracle", "_ref", "liblpopc_ref.so")
+_worker = {}
+
+
+def _ref_worker_init():
+    from oracle_lib import RefOracle
+    _worker["o"] = RefOracle(quadrotor_problem())
+
+
+def _ref_worker_eval(span):
+    lo, hi = span
+    g, v = _worker["o"].eval_g_jac_batch(_worker["X"][lo:hi], nthreads=1)
+    return float(v[:, 0].sum())
+
+
+class CpuPath:
+    """The reference's CPU implementation of the path on `threads` host cores.
+
+    kind "reference": the reference's OWN sources (oracle/_ref/liblpopc_ref.so, built from
+    /root/reference against oracle/ref_shim/ by oracle/ref_build.mk).  The reference is
+    single-threaded and not re-entrant (function-static caches), so the cores are used by forked
+    worker processes, each evaluating a contiguous share of the instances.
+    kind "port": the restatement (oracle/) with one std::thread per core, when no _ref was built."""
+
+    def __init__(self, op, X, threads):
+        self.X, self.threads = X, threads
+        from oracle_lib import Oracle
+        self.nnz = Oracle(op).nnz_jac
+        self.kind = "reference" if os.path.exists(REF_LIB) else "port"
+        if self.kind == "reference":
+            import multiprocessing as mp
+            _worker["X"] = X  # inherited by the forked workers
+            self.pool = mp.get_context("fork").Pool(threads, initializer=_ref_worker_init)
+            per = (len(X) + threads - 1) // threads
+            self.spans = [(i, min(len(X), i + per)) for i in range(0, len(X), per)]
+        else:
+            self.o = Oracle(op)
+
+    def step(self):
+        if self.kind == "reference":
+            self.pool.map(_ref_worker_eval, self.spans, chunksize=1)
+        else:
+            self.o.eval_g_jac_batch(self.X, nthreads=self.threads)
+
+    def close(self):
+        if self.kind == "reference":
+            self.pool.close()
+            self.pool.join()
+
+    def describe(self):
+        if self.kind == "reference":
+            return ("the reference's own sources (Core/LpNLPWrapper.cpp, LpFiniteDifferenceDerive.cpp, ... compiled against the "
+                    "Armadillo stand-in oracle/ref_shim), %d forked single-threaded workers" % self.threads)
+        return "oracle/ restatement of the reference path, %d host threads (no oracle/_ref build available)" % self.threads
+
+
 def cpu_reference_rate(op, X, threads, budget_s=10.0):
-    """nnz/s of the CPU restatement (oracle/) on `threads` host threads: the whole batch X,
-    repeated until about budget_s seconds of wall time have been spent."""
-    from oracle_lib import Oracle
-    o = Oracle(op)
-    o.eval_g_jac_batch(X[: min(len(X), 4 * threads)], nthreads=threads)  # warm-up
+    """(nnz/s, seconds, passes, CpuPath) over the whole batch X, repeated for about budget_s seconds."""
+    cp = CpuPath(op, X, threads)
+    cp.step()  # warm-up
     reps, t0 = 0, time.perf_counter()
     while True:
-        o.eval_g_jac_batch(X, nthreads=threads)
+        cp.step()
         reps += 1
         dt = time.perf_counter() - t0
         if dt >= budget_s:
             break
-    return o.nnz_jac * len(X) * reps / dt, dt, reps
+    cp.close()
+    return cp.nnz * len(X) * reps / dt, dt, reps, cp
 
 
 def run_reference(args, rank, world):
@@ -147,21 +202,22 @@ def run_reference(args, rank, world):
     threads = os.cpu_count() or 1
     sample = INSTANCES_PER_GPU
     X = make_inputs(op, pts, 0, sample)
-    for _ in range(args.warmup):
-        o.eval_g_jac_batch(X[:threads], nthreads=threads)
+    cp = CpuPath(op, X, threads)
+    for _ in range(max(1, args.warmup)):
+        cp.step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        o.eval_g_jac_batch(X, nthreads=threads)
+        cp.step()
     dt = time.perf_counter() - t0
+    cp.close()
     value = o.nnz_jac * sample * args.steps / dt
     line = {
         "impl": "reference", "metric": "collocation Jacobian nnz/s", "value": value, "unit": "nnz/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(o, world, sample_note="%d-instance sample per step" % sample),
-        "cpu_baseline": {"value": value, "unit": "nnz/s", "cores": threads, "kind": "port",
-                         "sample": "%d of %d quadrotor instances per step, all %d host threads (oracle/ restatement; the reference "
-                                   "needs Armadillo+IPOPT and is not buildable here)" % (sample, INSTANCES_PER_GPU, threads)},
+        "config": workload_config(o, world, sample_note="all %d instances of one GPU's share per step, on the host" % sample),
+        "cpu_baseline": {"value": value, "unit": "nnz/s", "cores": threads, "kind": cp.kind,
+                         "sample": "%d of %d quadrotor instances per step; %s" % (sample, INSTANCES_PER_GPU, cp.describe())},
         "e2e": {"value": value, "unit": "nnz/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -196,6 +252,14 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
+
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        # CPU leg first: it forks worker processes, which must happen before CUDA is initialised
+        from oracle_lib import Oracle as _O
+        _op = quadrotor_problem()
+        _X = make_inputs(_op, [_O(_op).tables(0)["points"]], 0, INSTANCES_PER_GPU)
+        cpu = cpu_reference_rate(_op, _X, os.cpu_count() or 1)
 
     import torch
     import torch.distributed as dist
@@ -326,7 +390,6 @@ def main():
         achieved = kbytes / (kavg_ms * 1e-3) / 1e9 if kavg_ms > 0 else 0.0
         # CPU baseline on a bounded sample, same box, all host threads
         threads = os.cpu_count() or 1
-        cpu_rate, cpu_dt, cpu_reps = (0.0, 0.0, 0) if args.no_cpu else cpu_reference_rate(op, X, threads)
         line = {
             "metric": "collocation Jacobian nnz/s", "value": value, "unit": "nnz/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_all / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -339,9 +402,9 @@ def main():
                          "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES, "bytes_per_launch": kbytes, "avg_launch_ms": kavg_ms,
                          "launches_timed": kern_cnt, "peak_source": peak_src,
                          "step_bytes": 8 * nb * (n + m + nnz), "step_frac": 8 * nb * (n + m + nnz) / (ms / args.steps * 1e-3) / 1e9 / peak},
-            "cpu_baseline": {"value": cpu_rate, "unit": "nnz/s", "cores": threads, "kind": "port",
-                             "sample": "all %d quadrotor instances x %d passes, %d host threads, %.1f s (oracle/ restatement of the "
-                                       "reference path; the reference itself is single-threaded)" % (nb, cpu_reps, threads, cpu_dt)},
+            "cpu_baseline": ({"value": cpu[0], "unit": "nnz/s", "cores": threads, "kind": cpu[3].kind,
+                              "sample": "all %d quadrotor instances x %d passes in %.1f s; %s" % (nb, cpu[2], cpu[1], cpu[3].describe())}
+                             if cpu else {"value": None, "unit": "nnz/s", "cores": threads, "kind": "skipped (--no-cpu)", "sample": ""}),
             "objective_checksum": float(np.sum(all_f)),
         }
         line.update(extras)

@@ -1,0 +1,60 @@
+#!/usr/bin/env python
+"""Generates tests/golden/*.npz from the REFERENCE'S OWN code (oracle/_ref/liblpopc_ref.so =
+/root/reference sources compiled against oracle/ref_shim/, see oracle/ref_build.mk).
+
+Runs only where /root/reference is mounted (this container); the fixtures travel with the repo so
+that the GPU box can check the CUDA path against reference outputs without the reference.
+One file per case of tests/cases.py: sizes, integer triplets, bounds, LGR tables, seeded inputs
+(tests/cases.py::inputs, seed 7) and the reference's f / grad / g / Jacobian / Hessian values there.
+
+    python oracle/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import cases  # noqa: E402
+from oracle_lib import RefOracle  # noqa: E402
+
+GOLDEN_CASES = cases.CASES + ["launch/u5x4", "hypersensitive/u40x3", "bryson_denham/u7x6"]
+SEED = 7
+
+
+def main():
+    out = os.path.join(ROOT, "tests", "golden")
+    os.makedirs(out, exist_ok=True)
+    for name in GOLDEN_CASES:
+        op = cases.build(name)
+        r = RefOracle(op)
+        guess, x, sigma, lam = cases.inputs(op, r, SEED)
+        jI, jJ = r.jac_structure()
+        hI, hJ = r.h_structure()
+        xl, xu, gl, gu = r.bounds()
+        d = dict(info=np.array(r.nlp_info()), jI=jI, jJ=jJ, hI=hI, hJ=hJ, xl=xl, xu=xu, gl=gl, gu=gu,
+                 ref_guess=r.guess(), guess=guess, x=x, sigma=np.array(sigma), lam=lam,
+                 f_guess=np.array(r.eval_f(guess)), f=np.array(r.eval_f(x)),
+                 grad_guess=r.eval_grad_f(guess), grad=r.eval_grad_f(x),
+                 g_guess=r.eval_g(guess), g=r.eval_g(x),
+                 jac_guess=r.eval_jac_g(guess), jac=r.eval_jac_g(x),
+                 hess=r.eval_h(x, sigma, lam))
+        for ip in range(len(op.phases)):
+            t = r.tables(ip)
+            d["points%d" % ip], d["weights%d" % ip] = t["points"], t["weights"]
+            d["doff_vals%d" % ip] = t["Doffdiag"][2]
+        if name == "launch":  # dependency probe + the sparse Hessian pattern it implies
+            d["dep"] = r.probe_dependencies(guess)
+            d["dep_info"] = np.array(r.nlp_info())
+            d["dep_hI"], d["dep_hJ"] = r.h_structure()
+            d["dep_hess"] = r.eval_h(x, sigma, lam)
+        path = os.path.join(out, name.replace("/", "__") + ".npz")
+        np.savez_compressed(path, **d)
+        print("%-28s n=%-6d m=%-6d nnz_jac=%-7d nnz_h=%-7d %6.1f KB" % ((name,) + r.nlp_info() + (os.path.getsize(path) / 1024,)))
+
+
+if __name__ == "__main__":
+    main()
