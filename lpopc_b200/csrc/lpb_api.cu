@@ -21,6 +21,7 @@
 #include <limits>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 // ---- functor registry ---------------------------------------------------------------------
@@ -313,6 +314,10 @@ struct lpb_handle {
     // evaluation staging
     DevBuf<double> d_x, d_g, d_vals, d_grad, d_lambda, d_sigma, d_hvals, d_f, d_scratch;
     DevBuf<int> d_dep;
+    // constant tail [L | C] of one instance's Jacobian values (mesh constants: -1/+1 of the linear
+    // rows and the Doffdiag entries), cached on the host at refresh
+    std::vector<double> h_ctail;
+    int host_fill_const = 1; // option "host_fill_const"
     lpb_handle() { std::memset(&pd, 0, sizeof pd); std::memset(&lay, 0, sizeof lay); std::memset(&ltab, 0, sizeof ltab); std::memset(&opts, 0, sizeof opts); }
     ~lpb_handle()
     {
@@ -460,6 +465,18 @@ static void refresh(lpb_handle* h)
     k_hess_structure<<<(unsigned)((L.nnz_h + 255) / 256), 256, 0, h->stream>>>(L, T, h->d_hI.p, h->d_hJ.p);
     h->launches += 2;
     CK(cudaGetLastError());
+    // host copy of the constant tail of the Jacobian values (LpNLPWrapper.cpp:242,:246-252,:715-718)
+    {
+        const size_t tail = (size_t)(L.nnz_jac - L.lin_val0);
+        h->h_ctail.assign(tail, 0.0);
+        for (int r = 0; r < P + Lp; ++r) { h->h_ctail[2 * r] = -1.0; h->h_ctail[2 * r + 1] = 1.0; }
+        if (L.ctot > 0) {
+            h->d_vals.reserve((size_t)L.nnz_jac);
+            h->launches += launch_fill_const(pd, h->stream, 1, h->d_vals.p);
+            CK(cudaMemcpyAsync(h->h_ctail.data() + (L.c0[0] - L.lin_val0), h->d_vals.p + L.c0[0], (size_t)L.ctot * sizeof(double),
+                               cudaMemcpyDeviceToHost, h->stream));
+        }
+    }
     CK(cudaStreamSynchronize(h->stream));
     h->fresh = true;
 }
@@ -805,13 +822,40 @@ int lpb_eval_g_jac_batch(lpb_handle* h, int nbatch, const double* x, double* g, 
     LPB_API_BEGIN(h)
     need_fresh(h);
     if (nbatch < 1 || !x) throw ApiError(LPB_ERR_INVALID, "bad argument");
-    h2d(h, h->d_x, x, (size_t)nbatch * h->pd.n);
-    if (g) h->d_g.reserve((size_t)nbatch * h->pd.m);
-    if (values) h->d_vals.reserve((size_t)nbatch * h->pd.nnz_jac);
+    const size_t n = (size_t)h->pd.n, m = (size_t)h->pd.m, nnz = (size_t)h->pd.nnz_jac;
+    h2d(h, h->d_x, x, (size_t)nbatch * n);
+    if (g) h->d_g.reserve((size_t)nbatch * m);
+    if (values) h->d_vals.reserve((size_t)nbatch * nnz);
+    // The tail [L | C] of every instance's values is a constant of the mesh: instead of writing it
+    // on the device and moving it over PCIe on every call, host threads copy it from the cached
+    // tail into the caller's array while the DMA engine brings back the x-dependent head [NL].
+    const size_t head = (size_t)h->pd.lin_val0, tail = nnz - head;
+    const bool host_tail = values && h->host_fill_const && tail > 0;
+    const int saved = h->opts.skip_const;
+    h->opts.skip_const = host_tail ? 1 : 0;
     int rc = lpb_eval_g_jac_dev(h, nbatch, h->d_x.p, g ? h->d_g.p : nullptr, values ? h->d_vals.p : nullptr);
+    h->opts.skip_const = saved;
     if (rc != LPB_OK) return rc;
-    if (g) d2h(h, g, h->d_g.p, (size_t)nbatch * h->pd.m);
-    if (values) d2h(h, values, h->d_vals.p, (size_t)nbatch * h->pd.nnz_jac);
+    if (g) d2h(h, g, h->d_g.p, (size_t)nbatch * m);
+    if (values && !host_tail) d2h(h, values, h->d_vals.p, (size_t)nbatch * nnz);
+    if (host_tail) {
+        if (head > 0)
+            CK(cudaMemcpy2DAsync(values, nnz * sizeof(double), h->d_vals.p, nnz * sizeof(double), head * sizeof(double), (size_t)nbatch,
+                                 cudaMemcpyDeviceToHost, h->stream));
+        unsigned hw = std::thread::hardware_concurrency();
+        int nt = (int)(hw ? hw : 1);
+        if (nt > 8) nt = 8;
+        if ((size_t)nbatch * tail < (size_t)1 << 16) nt = 1;
+        if (nt > nbatch) nt = nbatch;
+        const double* src = h->h_ctail.data();
+        auto fill = [=](int t) {
+            for (int b = t; b < nbatch; b += nt) std::memcpy(values + (size_t)b * nnz + head, src, tail * sizeof(double));
+        };
+        std::vector<std::thread> th;
+        for (int t = 1; t < nt; ++t) th.emplace_back(fill, t);
+        fill(0);
+        for (auto& t : th) t.join();
+    }
     CK(cudaStreamSynchronize(h->stream));
     LPB_API_END(h)
 }
@@ -887,6 +931,7 @@ int lpb_set_option_int(lpb_handle* h, const char* name, int value)
     if (!std::strcmp(name, "colour_split")) h->opts.colour_split = value;
     else if (!std::strcmp(name, "pair_split")) h->opts.pair_split = value;
     else if (!std::strcmp(name, "block")) h->opts.block = value;
+    else if (!std::strcmp(name, "host_fill_const")) h->host_fill_const = value;
     else if (!std::strcmp(name, "unroll_colours")) h->opts.unroll_colours = value;
     else if (!std::strcmp(name, "time_kernels")) h->time_kernels = value != 0;
     else throw ApiError(LPB_ERR_INVALID, std::string("unknown option ") + name);

@@ -76,6 +76,9 @@ struct LaunchOpts {
     int colour_split; // colour chunks (gridDim.y) of the Jacobian kernel; 0 = auto
     int pair_split;   // pair chunks of the Hessian kernel; 0 = auto
     int sm_count;
+    int skip_const;     // 1: do not write the constant tail [L | C] of the Jacobian values (the host-pointer
+                        // entry points fill it in the caller's array from a cached copy instead of moving it
+                        // over PCIe on every call)
     int unroll_colours; // Jacobian kernel variant: -1 = functor default (P::UNROLL_COLOURS), 0 = colour loop, 1 = unrolled
     // optional CUDA events recorded on the launch stream right before / after the dominant
     // node kernel (bench.py's live roofline measurement); null = no timing
