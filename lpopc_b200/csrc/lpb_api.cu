@@ -15,6 +15,10 @@
 #include "lpb_kernels.cuh"
 
 #include <cmath>
+#include <cstdint>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -302,6 +306,7 @@ struct lpb_handle {
     LaunchOpts opts;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t pipe[2] = {nullptr, nullptr}; // H2D / kernel / D2H pipeline of the host-pointer batch call
     long long launches = 0;
     std::string err;
     // live kernel timing (option "time_kernels"): one event pair per timed launch
@@ -324,6 +329,7 @@ struct lpb_handle {
         for (auto* v : {&timed_cons, &timed_hess})
             for (auto& pr : *v) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
         if (own_stream && stream) cudaStreamDestroy(stream);
+        for (cudaStream_t p : pipe) if (p) cudaStreamDestroy(p);
     }
 };
 
@@ -817,13 +823,27 @@ int lpb_eval_grad_f_batch(lpb_handle* h, int nbatch, const double* x, double* gr
     LPB_API_END(h)
 }
 
+// non-temporal copy of doubles (the destination is written once and next read by the caller, so
+// it should not be pulled into this core's cache first: no read-for-ownership traffic)
+static void stream_copy(double* dst, const double* src, size_t n)
+{
+#if defined(__SSE2__)
+    size_t i = 0;
+    if (((uintptr_t)dst & 15u) && n) { _mm_stream_si64((long long*)dst, *(const long long*)src); i = 1; }
+    for (; i + 2 <= n; i += 2) _mm_stream_pd(dst + i, _mm_loadu_pd(src + i));
+    if (i < n) _mm_stream_si64((long long*)(dst + i), *(const long long*)(src + i));
+#else
+    std::memcpy(dst, src, n * sizeof(double));
+#endif
+}
+
 int lpb_eval_g_jac_batch(lpb_handle* h, int nbatch, const double* x, double* g, double* values)
 {
     LPB_API_BEGIN(h)
     need_fresh(h);
     if (nbatch < 1 || !x) throw ApiError(LPB_ERR_INVALID, "bad argument");
     const size_t n = (size_t)h->pd.n, m = (size_t)h->pd.m, nnz = (size_t)h->pd.nnz_jac;
-    h2d(h, h->d_x, x, (size_t)nbatch * n);
+    h->d_x.reserve((size_t)nbatch * n);
     if (g) h->d_g.reserve((size_t)nbatch * m);
     if (values) h->d_vals.reserve((size_t)nbatch * nnz);
     // The tail [L | C] of every instance's values is a constant of the mesh: instead of writing it
@@ -831,32 +851,64 @@ int lpb_eval_g_jac_batch(lpb_handle* h, int nbatch, const double* x, double* g, 
     // tail into the caller's array while the DMA engine brings back the x-dependent head [NL].
     const size_t head = (size_t)h->pd.lin_val0, tail = nnz - head;
     const bool host_tail = values && h->host_fill_const && tail > 0;
-    const int saved = h->opts.skip_const;
-    h->opts.skip_const = host_tail ? 1 : 0;
-    int rc = lpb_eval_g_jac_dev(h, nbatch, h->d_x.p, g ? h->d_g.p : nullptr, values ? h->d_vals.p : nullptr);
-    h->opts.skip_const = saved;
-    if (rc != LPB_OK) return rc;
-    if (g) d2h(h, g, h->d_g.p, (size_t)nbatch * m);
-    if (values && !host_tail) d2h(h, values, h->d_vals.p, (size_t)nbatch * nnz);
+    std::vector<std::thread> th;
     if (host_tail) {
-        if (head > 0)
-            CK(cudaMemcpy2DAsync(values, nnz * sizeof(double), h->d_vals.p, nnz * sizeof(double), head * sizeof(double), (size_t)nbatch,
-                                 cudaMemcpyDeviceToHost, h->stream));
         unsigned hw = std::thread::hardware_concurrency();
         int nt = (int)(hw ? hw : 1);
-        if (nt > 8) nt = 8;
+        if (nt > 16) nt = 16;
         if ((size_t)nbatch * tail < (size_t)1 << 16) nt = 1;
         if (nt > nbatch) nt = nbatch;
         const double* src = h->h_ctail.data();
-        auto fill = [=](int t) {
-            for (int b = t; b < nbatch; b += nt) std::memcpy(values + (size_t)b * nnz + head, src, tail * sizeof(double));
-        };
-        std::vector<std::thread> th;
-        for (int t = 1; t < nt; ++t) th.emplace_back(fill, t);
-        fill(0);
-        for (auto& t : th) t.join();
+        for (int t = 0; t < nt; ++t)
+            th.emplace_back([=]() {
+                for (int b = t; b < nbatch; b += nt) stream_copy(values + (size_t)b * nnz + head, src, tail);
+#if defined(__SSE2__)
+                _mm_sfence();
+#endif
+            });
     }
-    CK(cudaStreamSynchronize(h->stream));
+    // chunked pipeline over two streams: H2D of chunk c+1 and the kernels of chunk c overlap the
+    // D2H of chunk c-1 (the D2H direction is the bottleneck of the whole call)
+    int nchunk = nbatch >= 64 ? 8 : 1;
+    const int per = (nbatch + nchunk - 1) / nchunk;
+    if (nchunk > 1 && !h->pipe[0]) {
+        CK(cudaStreamCreateWithFlags(&h->pipe[0], cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&h->pipe[1], cudaStreamNonBlocking));
+    }
+    const cudaStream_t user_stream = h->stream;
+    if (nchunk > 1) CK(cudaStreamSynchronize(user_stream)); // earlier work on the handle's stream comes first
+    const int saved = h->opts.skip_const;
+    h->opts.skip_const = host_tail ? 1 : 0;
+    int rc = LPB_OK;
+    std::string err;
+    try {
+        for (int c = 0, b0 = 0; b0 < nbatch; ++c, b0 += per) {
+            const int nb = nbatch - b0 < per ? nbatch - b0 : per;
+            const cudaStream_t st = nchunk > 1 ? h->pipe[c & 1] : user_stream;
+            h->stream = st;
+            CK(cudaMemcpyAsync(h->d_x.p + (size_t)b0 * n, x + (size_t)b0 * n, (size_t)nb * n * sizeof(double), cudaMemcpyHostToDevice, st));
+            rc = lpb_eval_g_jac_dev(h, nb, h->d_x.p + (size_t)b0 * n, g ? h->d_g.p + (size_t)b0 * m : nullptr,
+                                    values ? h->d_vals.p + (size_t)b0 * nnz : nullptr);
+            if (rc != LPB_OK) { err = h->err; break; }
+            if (g) CK(cudaMemcpyAsync(g + (size_t)b0 * m, h->d_g.p + (size_t)b0 * m, (size_t)nb * m * sizeof(double), cudaMemcpyDeviceToHost, st));
+            if (values && !host_tail)
+                CK(cudaMemcpyAsync(values + (size_t)b0 * nnz, h->d_vals.p + (size_t)b0 * nnz, (size_t)nb * nnz * sizeof(double), cudaMemcpyDeviceToHost, st));
+            if (host_tail && head > 0)
+                CK(cudaMemcpy2DAsync(values + (size_t)b0 * nnz, nnz * sizeof(double), h->d_vals.p + (size_t)b0 * nnz, nnz * sizeof(double),
+                                     head * sizeof(double), (size_t)nb, cudaMemcpyDeviceToHost, st));
+        }
+    } catch (...) {
+        h->stream = user_stream;
+        h->opts.skip_const = saved;
+        for (auto& t : th) t.join();
+        throw;
+    }
+    h->stream = user_stream;
+    h->opts.skip_const = saved;
+    for (auto& t : th) t.join();
+    if (nchunk > 1) { CK(cudaStreamSynchronize(h->pipe[0])); CK(cudaStreamSynchronize(h->pipe[1])); }
+    else CK(cudaStreamSynchronize(h->stream));
+    if (rc != LPB_OK) { h->err = err; return rc; }
     LPB_API_END(h)
 }
 
