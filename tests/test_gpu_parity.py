@@ -150,3 +150,93 @@ def test_fd_division_is_ieee(nlp_mod):
     """The Jacobian kernels divide by the per-colour step h through one shared reciprocal
     (FdDiv, lpb_kernels.cuh); every quotient must equal IEEE d / h bit for bit."""
     assert nlp_mod.selftest_fd_division(1 << 28, seed=12345) == 0
+
+
+# ---- BASELINE.json configurations at their full sizes ---------------------------------------------
+def _seeded_x(g, seed, nb=1):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    xl, xu, _, _ = g.get_bounds_info()
+    lo, hi = np.maximum(xl, -1.0), np.minimum(xu, 1.5)
+    hi = np.where(hi > lo, hi, lo + 1.0)
+    return rng.uniform(lo, hi, (nb, g.n))
+
+
+@pytest.mark.gpu
+def test_full_size_config2_orbit_raising_2000_nodes(nlp_mod):
+    """BASELINE config 2: single phase, 200 x 10 = 2000 LGR nodes (n = 14007)."""
+    from lpopc_b200 import examples
+    op = examples.orbit_raising(intervals=200, nodes=10)
+    o, g = Oracle(op), nlp_mod.TranscribedNLP(op)
+    assert g.get_nlp_info() == (o.n, o.m, o.nnz_jac, o.nnz_h) and o.n == 14007
+    for a, b in zip(g.eval_jac_g(values=False) + g.eval_h(values=False), o.jac_structure() + o.h_structure()):
+        assert np.array_equal(a, b)
+    _, x, sigma, lam = cases.inputs(op, o, 3)
+    gg, gv = g.eval_g_jac(x)
+    assert rel_err(gg, o.eval_g(x)) <= RTOL and rel_err(gv, o.eval_jac_g(x)) <= RTOL
+    assert rel_err(g.eval_grad_f(x), o.eval_grad_f(x)) <= RTOL
+    assert rel_err(g.eval_h(x, sigma, lam), o.eval_h(x, sigma, lam)) <= 1e-9
+
+
+@pytest.mark.gpu
+def test_full_size_config3_launch_4_phases_10k_variables(nlp_mod):
+    """BASELINE config 3: launch vehicle ascent, 4 phases x (25 x 10) nodes, 3 x 7 links (n = 10036)."""
+    from lpopc_b200 import examples
+    op = examples.launch(intervals=25, nodes=10)
+    o, g = Oracle(op), nlp_mod.TranscribedNLP(op)
+    assert g.get_nlp_info() == (o.n, o.m, o.nnz_jac, o.nnz_h) and (o.n, o.m, o.nnz_jac) == (10036, 8033, 166388)
+    for a, b in zip(g.eval_jac_g(values=False) + g.eval_h(values=False), o.jac_structure() + o.h_structure()):
+        assert np.array_equal(a, b)
+    _, x, sigma, lam = cases.inputs(op, o, 4)
+    gg, gv = g.eval_g_jac(x)
+    assert rel_err(gg, o.eval_g(x)) <= RTOL and rel_err(gv, o.eval_jac_g(x)) <= RTOL
+    assert abs(g.eval_f(x) - o.eval_f(x)) <= RTOL * max(1.0, abs(o.eval_f(x)))
+    assert rel_err(g.eval_h(x, sigma, lam), o.eval_h(x, sigma, lam)) <= 1e-9
+
+
+@pytest.mark.gpu
+def test_full_size_config4_4096_quadrotor_instances(nlp_mod):
+    """BASELINE config 4: 4096 instances on the 8 x 8 mesh.  A sample of instances is compared with the
+    oracle; every instance of the batch must equal its own single-instance evaluation (bit for bit),
+    and the mesh-constant tail of the values must be identical across instances."""
+    from lpopc_b200 import examples
+    op = examples.quadrotor(intervals=8, nodes=8)
+    o, g = Oracle(op), nlp_mod.TranscribedNLP(op)
+    assert (g.n, g.m, g.nnz_jac) == (1038, 769, 19970)
+    nb = 4096
+    X = _seeded_x(g, 5, nb)
+    X[:, -2], X[:, -1] = 0.0, 2.0
+    G, V = g.eval_g_jac_batch(X)
+    sample = [0, 1, 511, 512, 2047, 4095]
+    og, ov = o.eval_g_jac_batch(X[sample], nthreads=4)
+    assert rel_err(G[sample], og) <= RTOL and rel_err(V[sample], ov) <= RTOL
+    for b in sample:
+        g1, v1 = g.eval_g_jac(X[b])
+        assert np.array_equal(G[b], g1) and np.array_equal(V[b], v1)
+    tail = 6146  # 2 linear-row entries + 12 x 512 Doffdiag entries
+    assert np.array_equal(V[:, -tail:], np.broadcast_to(V[0, -tail:], (nb, tail)))
+    g.set_option("host_fill_const", 0)  # the all-device path must give the same array
+    G2, V2 = g.eval_g_jac_batch(X)
+    assert np.array_equal(G, G2) and np.array_equal(V, V2)
+    F = g.eval_f_batch(X)
+    for b in sample[:3]:
+        assert abs(F[b] - o.eval_f(X[b])) <= RTOL * max(1.0, abs(F[b]))
+
+
+@pytest.mark.gpu
+def test_full_size_config5_synthetic_100k_nodes(nlp_mod):
+    """BASELINE config 5: ns=20, nc=6 synthetic dynamics on 10000 x 10 = 100k LGR nodes
+    (n = 2.6 M, nnz_jac = 76 M): structure and values against the oracle, in full."""
+    from lpopc_b200 import examples
+    op = examples.synthetic20(intervals=10000, nodes=10)
+    o, g = Oracle(op), nlp_mod.TranscribedNLP(op)
+    assert g.get_nlp_info() == (o.n, o.m, o.nnz_jac, o.nnz_h) and (o.n, o.nnz_jac) == (2600022, 76000002)
+    for a, b in zip(g.eval_jac_g(values=False), o.jac_structure()):
+        assert np.array_equal(a, b)
+    for a, b in zip(g.eval_h(values=False), o.h_structure()):
+        assert np.array_equal(a, b)
+    x = _seeded_x(g, 7)[0]
+    x[-2], x[-1] = 0.0, 10.0
+    gg, gv = g.eval_g_jac(x)
+    assert rel_err(gg, o.eval_g(x)) <= RTOL
+    assert rel_err(gv, o.eval_jac_g(x)) <= RTOL
+    assert abs(g.eval_f(x) - o.eval_f(x)) <= RTOL * max(1.0, abs(o.eval_f(x)))
