@@ -386,8 +386,9 @@ def main():
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         ph = op.phases[0]
         N, ns, nc, npth = ph.GetTotalNodes(), len(ph.statemin), len(ph.controlmin), len(ph.pathmin)
-        # k_cons_jac per instance: reads x (n), writes the node rows of g and the node part of NL
-        kbytes = 8 * nb * (n + (ns + npth) * N + (ns + npth) * (ns + nc + 2) * N)
+        # k_cons_jac per instance: reads x (n), writes the node rows of g, the node part of NL and the
+        # constant segment C (ns copies of the Doffdiag values, fused into the kernel)
+        kbytes = 8 * nb * (n + (ns + npth) * N + (ns + npth) * (ns + nc + 2) * N + ns * sum(int(v) ** 2 for v in ph.nodesperinterval))
         kavg_ms = kern_ms / max(1, kern_cnt)
         achieved = kbytes / (kavg_ms * 1e-3) / 1e9 if kavg_ms > 0 else 0.0
         # CPU baseline on a bounded sample, same box, all host threads
