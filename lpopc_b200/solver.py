@@ -1,0 +1,358 @@
+"""Batched outer NLP solver for independent MPC-style OCP instances.
+
+The reference hands one NLP at a time to IPOPT on the host (Lpopc/src/Core/LpNLPSolver.cpp:13-54:
+tol = "Ipopt-tol" 1e-6, adaptive barrier).  For a batch of instances that share problem, mesh and
+sparsity pattern this module runs ONE primal-dual interior-point iteration for all instances in
+lockstep on the GPU: every callback an interior-point method needs (objective, gradient,
+constraints, Jacobian values, Lagrangian-Hessian values) is a device-resident batched call into the
+transcription kernels (`lpb_*_dev`), so x, lambda and the triplet values never leave HBM.
+
+Scope of this first version (stated, not hidden):
+  * linear algebra is library code -- dense batched Cholesky / triangular solves through
+    torch.linalg (cuSOLVER / cuBLAS), on the condensed system  S = J H^-1 J^T  with
+    H = W + Sigma + delta_w I; the transcription kernels are the product, this solver is the
+    first consumer of their device API;
+  * equality constraints (g_l == g_u) and variable bounds (log barrier, primal-dual); variables
+    with x_l == x_u are eliminated; inequality rows are accepted only when all their variables
+    are fixed (the duration row t_f - t_0 >= 0 of an MPC instance with fixed horizon);
+  * l1 merit function with backtracking line search, monotone barrier reduction (Fiacco-McCormick
+    as in IPOPT's default), per-instance Hessian regularisation delta_w driven by the Cholesky
+    status of each instance.
+
+The evaluator abstraction lets the same algorithm run against the CPU oracle in tests/ (parity of
+converged objectives); the product evaluator below is CUDA-only.
+"""
+import numpy as np
+import torch
+
+
+class CudaEvaluator:
+    """Device-resident batched callbacks of one TranscribedNLP (all tensors float64 on cuda)."""
+
+    def __init__(self, nlp):
+        self.nlp = nlp
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        nlp.set_stream(torch.cuda.current_stream().cuda_stream)
+        self.n, self.m, self.nnz_jac, self.nnz_h = nlp.get_nlp_info()
+        jI, jJ = nlp.eval_jac_g(values=False)
+        hI, hJ = nlp.eval_h(values=False)
+        self.jI, self.jJ = torch.from_numpy(jI.astype(np.int64)).to(self.device), torch.from_numpy(jJ.astype(np.int64)).to(self.device)
+        self.hI, self.hJ = torch.from_numpy(hI.astype(np.int64)).to(self.device), torch.from_numpy(hJ.astype(np.int64)).to(self.device)
+        self.evals = {"f": 0, "grad": 0, "g_jac": 0, "g": 0, "hess": 0}
+
+    def bounds(self):
+        return [torch.from_numpy(a).to(self.device) for a in self.nlp.get_bounds_info()]
+
+    def tensor(self, a):
+        if isinstance(a, torch.Tensor):
+            return a.to(device=self.device, dtype=torch.float64)
+        return torch.as_tensor(np.asarray(a, dtype=np.float64)).to(self.device)
+
+    def f(self, X):
+        out = torch.empty(X.shape[0], dtype=torch.float64, device=self.device)
+        self.nlp.eval_f_dev(X.shape[0], X.data_ptr(), out.data_ptr())
+        self.evals["f"] += 1
+        return out
+
+    def grad(self, X):
+        out = torch.empty_like(X)
+        self.nlp.eval_grad_f_dev(X.shape[0], X.data_ptr(), out.data_ptr())
+        self.evals["grad"] += 1
+        return out
+
+    def g(self, X):
+        out = torch.empty((X.shape[0], self.m), dtype=torch.float64, device=self.device)
+        self.nlp.eval_g_jac_dev(X.shape[0], X.data_ptr(), out.data_ptr(), None)
+        self.evals["g"] += 1
+        return out
+
+    def g_jac(self, X):
+        g = torch.empty((X.shape[0], self.m), dtype=torch.float64, device=self.device)
+        v = torch.empty((X.shape[0], self.nnz_jac), dtype=torch.float64, device=self.device)
+        self.nlp.eval_g_jac_dev(X.shape[0], X.data_ptr(), g.data_ptr(), v.data_ptr())
+        self.evals["g_jac"] += 1
+        return g, v
+
+    def hess(self, X, sigma, lam):
+        v = torch.empty((X.shape[0], self.nnz_h), dtype=torch.float64, device=self.device)
+        self.nlp.eval_h_dev(X.shape[0], X.data_ptr(), sigma.data_ptr(), lam.data_ptr(), v.data_ptr())
+        self.evals["hess"] += 1
+        return v
+
+
+class BatchedIPM:
+    """Lockstep primal-dual interior-point method over a batch of instances of one NLP."""
+
+    def __init__(self, ev, tol=1e-6, max_iter=100, mu0=0.1, rho=1e3, verbose=False):
+        self.ev, self.tol, self.max_iter, self.mu0, self.rho, self.verbose = ev, tol, max_iter, mu0, rho, verbose
+        self.n, self.m = ev.n, ev.m
+
+    # ---- problem structure shared by all instances ------------------------------------------------
+    def _setup(self, xl, xu, gl, gu):
+        ev, dev = self.ev, self.ev.device
+        fixed = xl[0] == xu[0]
+        if not bool(((xl == xu) == fixed.unsqueeze(0)).all()):
+            raise ValueError("the set of fixed variables must be the same for every instance")
+        self.free = torch.nonzero(~fixed).squeeze(1)
+        self.nf = int(self.free.numel())
+        colmap = torch.full((self.n,), -1, dtype=torch.int64, device=dev)
+        colmap[self.free] = torch.arange(self.nf, device=dev)
+        eq = gl == gu
+        # inequality rows: only constant ones (all their variables fixed) are supported
+        ineq_rows = torch.nonzero(~eq).squeeze(1)
+        if ineq_rows.numel():
+            in_ineq = torch.isin(ev.jI, ineq_rows)
+            if bool((colmap[ev.jJ[in_ineq]] >= 0).any()):
+                raise NotImplementedError("inequality constraint rows with free variables need slacks (not in this version)")
+        self.eq = torch.nonzero(eq).squeeze(1)
+        self.me = int(self.eq.numel())
+        self.ineq_rows = ineq_rows
+        rowmap = torch.full((self.m,), -1, dtype=torch.int64, device=dev)
+        rowmap[self.eq] = torch.arange(self.me, device=dev)
+        r, c = rowmap[ev.jI], colmap[ev.jJ]
+        self.j_sel = torch.nonzero((r >= 0) & (c >= 0)).squeeze(1)
+        self.j_flat = r[self.j_sel] * self.nf + c[self.j_sel]
+        hr, hc = colmap[ev.hI], colmap[ev.hJ]
+        sel = torch.nonzero((hr >= 0) & (hc >= 0)).squeeze(1)
+        off = sel[hr[sel] != hc[sel]]
+        self.h_sel = torch.cat([sel, off])  # lower triangle + its mirror
+        self.h_flat = torch.cat([hr[sel] * self.nf + hc[sel], hc[off] * self.nf + hr[off]])
+        self.c_target = gl[self.eq]
+
+    def _dense_jac(self, vals):
+        B = vals.shape[0]
+        J = torch.zeros((B, self.me * self.nf), dtype=torch.float64, device=vals.device)
+        J.index_add_(1, self.j_flat, vals[:, self.j_sel])  # duplicate triplets sum (TNLP contract)
+        return J.view(B, self.me, self.nf)
+
+    def _dense_hess(self, vals):
+        B = vals.shape[0]
+        H = torch.zeros((B, self.nf * self.nf), dtype=torch.float64, device=vals.device)
+        H.index_add_(1, self.h_flat, vals[:, self.h_sel])
+        return H.view(B, self.nf, self.nf)
+
+    # ---- solve ---------------------------------------------------------------------------------------
+    def solve(self, x0, xl=None, xu=None, chunk=1024):
+        """x0: [B, n] starting points; xl/xu: per-instance bounds [B, n] (default: the problem's).
+        Instances are processed `chunk` at a time (the dense condensed systems of one chunk must fit
+        in HBM: about 40 MB per quadrotor instance).  Returns dict(x, obj, status, iters, kkt_error, lam)."""
+        B = len(x0)
+        outs = []
+        for b0 in range(0, B, chunk):
+            sl_ = slice(b0, min(B, b0 + chunk))
+            outs.append(self._solve_compacting(x0[sl_], None if xl is None else xl[sl_], None if xu is None else xu[sl_]))
+        return {k: torch.cat([o[k] for o in outs]) for k in outs[0]}
+
+    def _solve_compacting(self, x0, xl, xu):
+        """Lockstep iterations over the instances still active: whenever fewer than half of the current
+        sub-batch is unconverged, the iteration is suspended and resumed on the unconverged instances
+        only (state carried over), so stragglers do not pay for the whole batch's linear algebra."""
+        ev = self.ev
+        B = len(x0)
+        bxl, bxu, _, _ = ev.bounds()
+        XL = bxl.expand(B, -1) if xl is None else ev.tensor(xl)
+        XU = bxu.expand(B, -1) if xu is None else ev.tensor(xu)
+        res = self._solve_chunk(x0, XL, XU, None, 0)
+        out = {k: v.clone() for k, v in res.items() if k != "state"}
+        ids = torch.arange(B, device=out["x"].device)
+        while res["state"] is not None:
+            st = res["state"]
+            act = st["active"]
+            ids = ids[act]
+            sub = {k: (v[act] if isinstance(v, torch.Tensor) and v.dim() > 0 and v.shape[0] == act.shape[0] else v) for k, v in st.items()}
+            res = self._solve_chunk(sub["X"], XL[ids], XU[ids], sub, st["it"])
+            for k in out:
+                out[k][ids] = res[k]
+        return out
+
+    def _solve_chunk(self, x0, xl, xu, state, it0):
+        ev = self.ev
+        X = ev.tensor(x0).clone()
+        B = X.shape[0]
+        _, _, gl, gu = ev.bounds()
+        self._setup(xl, xu, gl, gu)
+        F, nf, me = self.free, self.nf, self.me
+        fixed_mask = torch.ones(self.n, dtype=torch.bool, device=X.device)
+        fixed_mask[F] = False
+        X[:, fixed_mask] = xl[:, fixed_mask]
+        lo, hi = xl[:, F], xu[:, F]
+        hasL, hasU = torch.isfinite(lo), torch.isfinite(hi)
+        if state is None:
+            # push the starting point into the interior (IPOPT bound_push / bound_frac = 1e-2)
+            xf = X[:, F]
+            pl = torch.minimum(1e-2 * torch.clamp(lo.abs(), min=1.0), 1e-2 * (hi - lo))
+            pu = torch.minimum(1e-2 * torch.clamp(hi.abs(), min=1.0), 1e-2 * (hi - lo))
+            xf = torch.where(hasL & hasU, torch.minimum(torch.maximum(xf, lo + pl), hi - pu), xf)
+            xf = torch.where(hasL & ~hasU, torch.maximum(xf, lo + 1e-2 * torch.clamp(lo.abs(), min=1.0)), xf)
+            xf = torch.where(~hasL & hasU, torch.minimum(xf, hi - 1e-2 * torch.clamp(hi.abs(), min=1.0)), xf)
+            X[:, F] = xf
+            lam = torch.zeros((B, self.m), dtype=torch.float64, device=X.device)
+            zL = torch.where(hasL, torch.ones_like(lo), torch.zeros_like(lo))
+            zU = torch.where(hasU, torch.ones_like(hi), torch.zeros_like(hi))
+            mu = torch.full((B,), self.mu0, dtype=torch.float64, device=X.device)
+            nu = torch.full((B,), 1.0, dtype=torch.float64, device=X.device)  # l1 penalty
+            dw_last = torch.zeros(B, dtype=torch.float64, device=X.device)
+            iters = torch.zeros(B, dtype=torch.int64, device=X.device)
+        else:
+            lam, zL, zU, mu, nu, dw_last, iters = (state[k] for k in ("lam", "zL", "zU", "mu", "nu", "dw_last", "iters"))
+        done = torch.zeros(B, dtype=torch.bool, device=X.device)
+        failed = torch.zeros(B, dtype=torch.bool, device=X.device)
+        sigma1 = torch.ones(B, dtype=torch.float64, device=X.device)
+        kkt0 = torch.full((B,), float("inf"), dtype=torch.float64, device=X.device)
+        inf = float("inf")
+        sl = lambda x: torch.where(hasL, x - lo, torch.ones_like(x))  # noqa: E731
+        su = lambda x: torch.where(hasU, hi - x, torch.ones_like(x))  # noqa: E731
+
+        def barrier_obj(Xt, mu_):
+            xt = Xt[:, F]
+            phi = ev.f(Xt)
+            phi = phi - mu_ * (torch.where(hasL, torch.log(sl(xt)), torch.zeros_like(xt)).sum(1)
+                               + torch.where(hasU, torch.log(su(xt)), torch.zeros_like(xt)).sum(1))
+            c = ev.g(Xt)[:, self.eq] - self.c_target
+            return phi, c.abs().sum(1)
+
+        suspended = None
+        for it in range(it0, self.max_iter):
+            g, jv = ev.g_jac(X)
+            gradf = ev.grad(X)[:, F]
+            c = g[:, self.eq] - self.c_target
+            J = self._dense_jac(jv)
+            xf = X[:, F]
+            sL, sU = sl(xf), su(xf)
+            lam_eq = lam[:, self.eq]
+            rd = gradf + torch.bmm(J.transpose(1, 2), lam_eq.unsqueeze(2)).squeeze(2) - zL + zU
+            compL = torch.where(hasL, sL * zL, torch.zeros_like(sL))
+            compU = torch.where(hasU, sU * zU, torch.zeros_like(sU))
+            # scaled optimality error (IPOPT eq. (5)-(6)), smax = 100
+            nz = (hasL.sum(1) + hasU.sum(1)).clamp(min=1)
+            s_d = torch.clamp((lam_eq.abs().sum(1) + zL.sum(1) + zU.sum(1)) / (me + nz), min=100.0) / 100.0
+            s_c = torch.clamp((zL.sum(1) + zU.sum(1)) / nz, min=100.0) / 100.0
+
+            def err(mu_):
+                return torch.stack([rd.abs().amax(1) / s_d, c.abs().amax(1),
+                                    torch.maximum((compL - torch.where(hasL, mu_.unsqueeze(1), 0.0)).abs().amax(1),
+                                                  (compU - torch.where(hasU, mu_.unsqueeze(1), 0.0)).abs().amax(1)) / s_c]).amax(0)
+
+            e0 = err(torch.zeros_like(mu))
+            kkt0 = torch.where(done, kkt0, e0)
+            newly = (~done) & (e0 <= self.tol)
+            done |= newly
+            if self.verbose:
+                print("it %3d  active %4d  max E0 %.3e  mu[min,max] %.1e %.1e  |c|max %.2e  dw max %.1e"
+                      % (it, int((~done).sum()), float(e0[~done].max()) if (~done).any() else 0.0, float(mu.min()), float(mu.max()),
+                         float(c.abs().max()), float(dw_last.max())))
+            if bool(done.all()):
+                break
+            n_act = int((~done).sum())
+            if B >= 16 and 2 * n_act < B:  # resume on the unconverged instances only
+                suspended = {"X": X, "lam": lam, "zL": zL, "zU": zU, "mu": mu, "nu": nu, "dw_last": dw_last, "iters": iters,
+                             "active": ~done, "it": it}
+                break
+            # barrier update (monotone): while E_mu <= kappa_eps * mu
+            for _ in range(4):
+                emu = err(mu)
+                upd = (~done) & (emu <= 10.0 * mu) & (mu > self.tol / 10.0)
+                if not bool(upd.any()):
+                    break
+                mu = torch.where(upd, torch.clamp(torch.minimum(0.2 * mu, mu ** 1.5), min=self.tol / 10.0), mu)
+            mu_c = mu.unsqueeze(1)
+            # Hessian of the Lagrangian (exact, finite differences of the reference scheme) + Sigma
+            W = self._dense_hess(ev.hess(X, sigma1, lam))
+            Sigma = torch.where(hasL, zL / sL, torch.zeros_like(sL)) + torch.where(hasU, zU / sU, torch.zeros_like(sU))
+            rhs1 = gradf + torch.bmm(J.transpose(1, 2), lam_eq.unsqueeze(2)).squeeze(2) \
+                - torch.where(hasL, mu_c / sL, torch.zeros_like(sL)) + torch.where(hasU, mu_c / sU, torch.zeros_like(sU))
+            # factor H_rho = W + Sigma + rho J^T J + dw I.  Adding rho J^T (J dx + c) = 0 to the first
+            # block row leaves (dx, dlam) unchanged, and by Debreu's lemma H_rho is positive definite for
+            # large rho exactly when the Hessian is positive definite on the null space of J -- the
+            # inertia condition an interior-point step needs -- so the Cholesky status of each instance
+            # drives its own regularisation dw (raised only for genuine negative curvature).
+            rho = self.rho
+            JtJ = torch.bmm(J.transpose(1, 2), J)
+            rhs1 = rhs1 + rho * torch.bmm(J.transpose(1, 2), c.unsqueeze(2)).squeeze(2)
+            dw = torch.where(dw_last > 0, dw_last / 3.0, torch.zeros_like(dw_last))
+            dw = torch.where(dw < 1e-9, torch.zeros_like(dw), dw)
+            Hd = W + rho * JtJ
+            diag = torch.arange(nf, device=X.device)
+            base_diag = Hd[:, diag, diag] + Sigma
+            for _try in range(40):
+                Hd[:, diag, diag] = base_diag + dw.unsqueeze(1)
+                Lh, info = torch.linalg.cholesky_ex(Hd)
+                bad = (info != 0) & (~done)
+                if not bool(bad.any()):
+                    break
+                dw = torch.where(bad, torch.where(dw == 0, torch.full_like(dw, 1e-4), dw * (100.0 if _try < 2 else 8.0)), dw)
+            dw_last = torch.where(done, dw_last, dw)
+            # condensed system: S dlam = c - J H^-1 rhs1 ... solve [H J^T; J 0][dx; dlam] = -[rhs1; c]
+            Y = torch.cholesky_solve(torch.cat([J.transpose(1, 2), rhs1.unsqueeze(2)], dim=2), Lh)  # H^-1 [J^T | rhs1]
+            HiJt, Hir = Y[:, :, :me], Y[:, :, me]
+            S = torch.bmm(J, HiJt)
+            S[:, torch.arange(me, device=X.device), torch.arange(me, device=X.device)] += 1e-12
+            Ls, info_s = torch.linalg.cholesky_ex(S)
+            bad_s = (info_s != 0) & (~done)
+            if bool(bad_s.any()):  # rank-deficient Jacobian: regularise the (2,2) block harder
+                S[bad_s] += 1e-8 * torch.eye(me, dtype=torch.float64, device=X.device)
+                Ls, info_s = torch.linalg.cholesky_ex(S)
+                failed |= (info_s != 0) & (~done)
+            rhs2 = c - torch.bmm(J, Hir.unsqueeze(2)).squeeze(2)
+            dlam = torch.cholesky_solve(rhs2.unsqueeze(2), Ls).squeeze(2)       # S dlam = c - J H^-1 rhs1
+            dx = -(Hir + torch.bmm(HiJt, dlam.unsqueeze(2)).squeeze(2))         # dx = -H^-1 (rhs1 + J^T dlam)
+            dzL = torch.where(hasL, mu_c / sL - zL - zL / sL * dx, torch.zeros_like(dx))
+            dzU = torch.where(hasU, mu_c / sU - zU + zU / sU * dx, torch.zeros_like(dx))
+            # fraction to the boundary
+            tau = torch.clamp(1.0 - mu, min=0.99).unsqueeze(1)
+            ratio = torch.full_like(dx, inf)
+            ratio = torch.where(hasL & (dx < 0), -tau * sL / dx, ratio)
+            ratio = torch.minimum(ratio, torch.where(hasU & (dx > 0), tau * sU / dx, torch.full_like(dx, inf)))
+            a_max = torch.clamp(ratio.amin(1), max=1.0)
+            rz = torch.full_like(dx, inf)
+            rz = torch.where(hasL & (dzL < 0), -tau * zL / dzL, rz)
+            rz = torch.minimum(rz, torch.where(hasU & (dzU < 0), -tau * zU / dzU, torch.full_like(dx, inf)))
+            a_z = torch.clamp(rz.amin(1), max=1.0)
+            # l1 merit: phi_mu(x) + nu |c|_1, Armijo backtracking
+            lam_new_inf = (lam_eq + dlam).abs().amax(1)
+            nu = torch.where(nu < lam_new_inf + 1.0, lam_new_inf * 1.5 + 1.0, nu)
+            gphi = gradf - torch.where(hasL, mu_c / sL, torch.zeros_like(sL)) + torch.where(hasU, mu_c / sU, torch.zeros_like(sU))
+            c1 = c.abs().sum(1)
+            dphi = (gphi * dx).sum(1) - nu * c1
+            phi0, _ = barrier_obj(X, mu)
+            merit0 = phi0 + nu * c1
+            alpha = a_max.clone()
+            accepted = done.clone()
+            Xn = X.clone()
+            for _ls in range(25):
+                Xt = X.clone()
+                Xt[:, F] = xf + alpha.unsqueeze(1) * dx
+                phit, ct = barrier_obj(Xt, mu)
+                ok = (phit + nu * ct <= merit0 + 1e-8 * alpha * torch.clamp(dphi, max=0.0) + 1e-12 * merit0.abs()) & torch.isfinite(phit)
+                take = ok & ~accepted
+                Xn[take] = Xt[take]
+                accepted |= take
+                if bool(accepted.all()):
+                    break
+                alpha = torch.where(accepted, alpha, alpha * 0.5)
+            # instances whose line search failed: take the tiny step anyway and raise dw next time
+            stuck = ~accepted
+            if bool(stuck.any()):
+                Xt = X.clone()
+                Xt[:, F] = xf + alpha.unsqueeze(1) * dx
+                Xn[stuck] = Xt[stuck]
+                dw_last = torch.where(stuck, torch.clamp(dw_last * 100.0, min=1e-2), dw_last)
+            act = (~done).unsqueeze(1)
+            a_col = alpha.unsqueeze(1)
+            X = torch.where(act, Xn, X)
+            lam_eq_new = lam_eq + a_col * dlam
+            lam_full = lam.clone()
+            lam_full[:, self.eq] = lam_eq_new
+            lam = torch.where(act, lam_full, lam)
+            zL = torch.where(act, zL + a_z.unsqueeze(1) * dzL, zL)
+            zU = torch.where(act, zU + a_z.unsqueeze(1) * dzU, zU)
+            # keep z within [mu/(k s), k mu/s] (IPOPT eq. (16), kappa_Sigma = 1e10)
+            xf2 = X[:, F]
+            sL2, sU2 = sl(xf2), su(xf2)
+            zL = torch.where(hasL, torch.maximum(torch.minimum(zL, 1e10 * mu_c / sL2), mu_c / (1e10 * sL2)), zL)
+            zU = torch.where(hasU, torch.maximum(torch.minimum(zU, 1e10 * mu_c / sU2), mu_c / (1e10 * sU2)), zU)
+            iters += (~done).to(torch.int64)
+        obj = ev.f(X)
+        status = torch.where(done, torch.zeros_like(iters), torch.ones_like(iters))
+        status = torch.where(failed & ~done, torch.full_like(iters, 2), status)
+        return {"x": X, "obj": obj, "status": status, "iters": iters, "kkt_error": kkt0, "lam": lam, "state": suspended}

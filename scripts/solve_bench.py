@@ -1,0 +1,62 @@
+#!/usr/bin/env python
+"""Batched OCP solves/s: B quadrotor (or cart-pole) MPC instances with varied initial states solved
+to KKT tolerance by lpopc_b200.solver.BatchedIPM on one GPU, every NLP callback a device-resident
+call into the transcription kernels.  Prints one JSON line.
+
+  python scripts/solve_bench.py quadrotor 1024 --chunk 1024
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("problem")
+    ap.add_argument("nbatch", type=int)
+    ap.add_argument("--chunk", type=int, default=1024)
+    ap.add_argument("--tol", type=float, default=1e-6)
+    ap.add_argument("--probe", type=int, default=1, help="run the NaN dependency probe first (sparser Hessian pattern), like the reference")
+    ap.add_argument("--verbose", action="store_true")
+    args = ap.parse_args()
+    import torch
+    from lpopc_b200 import examples, nlp, solver
+    from solver_cpu import mpc_bounds, mpc_instances
+    from oracle_lib import Oracle  # LGR points for the guess only (host, outside the timing)
+    op = getattr(examples, args.problem)(intervals=8, nodes=8)
+    pts = [Oracle(op).tables(0)["points"]]
+    ph = op.phases[0]
+    nominal = np.array([ph.stateguess[j][0] for j in range(len(ph.statemin))])
+    rng = np.random.Generator(np.random.PCG64(5))
+    x0s = nominal + 0.2 * rng.uniform(-1, 1, (args.nbatch, nominal.size))
+    X0 = mpc_instances(op, pts, x0s)
+    g = nlp.TranscribedNLP(op)
+    if args.probe:
+        g.probe_dependencies(X0[0])
+    ev = solver.CudaEvaluator(g)
+    XL, XU = mpc_bounds(ev, op, x0s)
+    ipm = solver.BatchedIPM(ev, tol=args.tol, max_iter=100, verbose=args.verbose)
+    ipm.solve(X0[:8], XL[:8], XU[:8])  # warm-up (cuSOLVER handles, kernels)
+    torch.cuda.synchronize()
+    l0, t0 = g.kernel_launches, time.perf_counter()
+    r = ipm.solve(X0, XL, XU, chunk=args.chunk)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    ok = int((r["status"] == 0).sum().item())
+    print(json.dumps({"metric": "batched OCP solves/s", "value": ok / dt, "unit": "solves/s", "problem": args.problem, "instances": args.nbatch,
+                      "converged": ok, "seconds": dt, "iters_mean": float(r["iters"].double().mean().item()), "iters_max": int(r["iters"].max().item()),
+                      "kkt_error_max": float(r["kkt_error"].max().item()), "objective_mean": float(r["obj"].mean().item()),
+                      "n": ev.n, "m": ev.m, "nnz_jac": ev.nnz_jac, "nnz_h": ev.nnz_h, "transcription_kernel_launches": g.kernel_launches - l0,
+                      "tol": args.tol, "chunk": args.chunk, "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9}))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,68 @@
+"""Batched interior-point solver (lpopc_b200/solver.py): convergence on the CPU
+evaluator, and converged objectives of the CUDA path within 1e-8 relative of the same algorithm
+run on the CPU restatement of the reference path (north_star tolerance)."""
+import numpy as np
+import pytest
+import torch
+
+from lpopc_b200 import examples, solver
+from solver_cpu import OracleEvaluator, mpc_bounds, mpc_instances
+
+
+def _instances(op, ev_cpu, nb, spread, seed):
+    pts = [ev_cpu.o.tables(0)["points"]]
+    ph = op.phases[0]
+    nominal = np.array([ph.stateguess[j][0] for j in range(len(ph.statemin))])
+    rng = np.random.Generator(np.random.PCG64(seed))
+    x0s = nominal + spread * rng.uniform(-1, 1, (nb, nominal.size))
+    return x0s, mpc_instances(op, pts, x0s)
+
+
+def test_ipm_converges_on_cartpole_cpu():
+    op = examples.cartpole(intervals=4, nodes=5)
+    ev = OracleEvaluator(op)
+    x0s, X0 = _instances(op, ev, 3, 0.1, 0)
+    XL, XU = mpc_bounds(ev, op, x0s)
+    r = solver.BatchedIPM(ev, tol=1e-6, max_iter=60).solve(X0, XL, XU)
+    assert int(r["status"].abs().sum()) == 0 and float(r["kkt_error"].max()) <= 1e-6
+    # feasibility of the returned points and fixed initial states
+    g = ev.g(r["x"])
+    _, _, gl, gu = ev.bounds()
+    eq = gl == gu
+    assert float((g[:, eq] - gl[eq]).abs().max()) <= 1e-6
+    N = op.phases[0].GetTotalNodes()
+    assert np.allclose(r["x"][:, torch.arange(4) * (N + 1)].numpy(), x0s, atol=0, rtol=0)
+    # a perturbed start converges to the same objective
+    r2 = solver.BatchedIPM(ev, tol=1e-7, max_iter=80).solve(X0 + 0.01, XL, XU)
+    r1 = solver.BatchedIPM(ev, tol=1e-7, max_iter=80).solve(X0, XL, XU)
+    assert np.allclose(r1["obj"].numpy(), r2["obj"].numpy(), rtol=1e-7)
+
+
+def test_ipm_rejects_unsupported_inequalities():
+    op = examples.bryson_denham()  # free final time: the duration row has free variables
+    ev = OracleEvaluator(op)
+    X0 = op.guess([ev.o.tables(0)["points"]])[None, :]
+    with pytest.raises(NotImplementedError):
+        solver.BatchedIPM(ev).solve(X0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("problem,kw,nb,spread", [("cartpole", dict(intervals=8, nodes=8), 64, 0.1), ("quadrotor", dict(intervals=8, nodes=8), 32, 0.2)])
+def test_gpu_solves_match_cpu_reference_objectives(problem, kw, nb, spread):
+    from lpopc_b200 import nlp
+    op = getattr(examples, problem)(**kw)
+    ev_cpu = OracleEvaluator(op, threads=8)
+    x0s, X0 = _instances(op, ev_cpu, nb, spread, 5)
+    g = nlp.TranscribedNLP(op)
+    ev_gpu = solver.CudaEvaluator(g)
+    XL, XU = mpc_bounds(ev_gpu, op, x0s)
+    l0 = g.kernel_launches
+    rg = solver.BatchedIPM(ev_gpu, tol=1e-7, max_iter=80).solve(X0, XL, XU)
+    assert g.kernel_launches > l0
+    assert int(rg["status"].abs().sum().item()) == 0
+    sample = [0, 1, nb - 1]
+    XLc, XUc = mpc_bounds(ev_cpu, op, x0s[sample])
+    rc = solver.BatchedIPM(ev_cpu, tol=1e-7, max_iter=80).solve(X0[sample], XLc, XUc)
+    assert int(rc["status"].abs().sum()) == 0
+    og, oc = rg["obj"].cpu().numpy()[sample], rc["obj"].numpy()
+    assert np.max(np.abs(og - oc) / np.maximum(1.0, np.abs(oc))) <= 1e-8
