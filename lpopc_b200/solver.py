@@ -80,6 +80,25 @@ class CudaEvaluator:
         return v
 
 
+def blocked_cholesky_ex(A, split=512):
+    """Batched lower Cholesky factor with a 2 x 2 block recursion above `split` rows: the batched
+    library factorisation is several times slower per flop beyond ~1000 rows than below, while the
+    off-diagonal work (triangular solve + symmetric update) runs at GEMM speed.  Returns (L, info)
+    like torch.linalg.cholesky_ex (info != 0: not positive definite)."""
+    n = A.shape[-1]
+    if n <= split:
+        return torch.linalg.cholesky_ex(A)
+    h = n // 2
+    L11, i1 = blocked_cholesky_ex(A[:, :h, :h], split)
+    ok = (i1 == 0).view(-1, 1, 1)
+    L11s = torch.where(ok, L11, torch.eye(h, dtype=A.dtype, device=A.device).expand_as(L11))  # keep failed instances finite
+    L21 = torch.linalg.solve_triangular(L11s, A[:, h:, :h].transpose(1, 2), upper=False).transpose(1, 2)
+    L22, i2 = blocked_cholesky_ex(A[:, h:, h:] - torch.bmm(L21, L21.transpose(1, 2)), split)
+    L = torch.zeros_like(A)
+    L[:, :h, :h], L[:, h:, :h], L[:, h:, h:] = L11s, L21, L22
+    return L, torch.where(i1 != 0, i1, i2)
+
+
 class BatchedIPM:
     """Lockstep primal-dual interior-point method over a batch of instances of one NLP."""
 
@@ -276,26 +295,29 @@ class BatchedIPM:
             base_diag = Hd[:, diag, diag] + Sigma
             for _try in range(40):
                 Hd[:, diag, diag] = base_diag + dw.unsqueeze(1)
-                Lh, info = torch.linalg.cholesky_ex(Hd)
+                Lh, info = blocked_cholesky_ex(Hd)
                 bad = (info != 0) & (~done)
                 if not bool(bad.any()):
                     break
                 dw = torch.where(bad, torch.where(dw == 0, torch.full_like(dw, 1e-4), dw * (100.0 if _try < 2 else 8.0)), dw)
             dw_last = torch.where(done, dw_last, dw)
-            # condensed system: S dlam = c - J H^-1 rhs1 ... solve [H J^T; J 0][dx; dlam] = -[rhs1; c]
-            Y = torch.cholesky_solve(torch.cat([J.transpose(1, 2), rhs1.unsqueeze(2)], dim=2), Lh)  # H^-1 [J^T | rhs1]
-            HiJt, Hir = Y[:, :, :me], Y[:, :, me]
-            S = torch.bmm(J, HiJt)
-            S[:, torch.arange(me, device=X.device), torch.arange(me, device=X.device)] += 1e-12
-            Ls, info_s = torch.linalg.cholesky_ex(S)
+            # condensed system of [H J^T; J 0][dx; dlam] = -[rhs1; c] with H = L L^T:
+            #   Y = L^-1 J^T, y = L^-1 rhs1, S = Y^T Y, S dlam = c - Y^T y, dx = -L^-T (y + Y dlam)
+            Yr = torch.linalg.solve_triangular(Lh, torch.cat([J.transpose(1, 2), rhs1.unsqueeze(2)], dim=2), upper=False)
+            Y, y = Yr[:, :, :me], Yr[:, :, me:]
+            S = torch.bmm(Y.transpose(1, 2), Y)
+            dS = torch.arange(me, device=X.device)
+            S[:, dS, dS] += 1e-12
+            Ls, info_s = blocked_cholesky_ex(S)
             bad_s = (info_s != 0) & (~done)
             if bool(bad_s.any()):  # rank-deficient Jacobian: regularise the (2,2) block harder
-                S[bad_s] += 1e-8 * torch.eye(me, dtype=torch.float64, device=X.device)
-                Ls, info_s = torch.linalg.cholesky_ex(S)
+                S[:, dS, dS] += torch.where(bad_s, 1e-8, 0.0).unsqueeze(1)
+                Ls, info_s = blocked_cholesky_ex(S)
                 failed |= (info_s != 0) & (~done)
-            rhs2 = c - torch.bmm(J, Hir.unsqueeze(2)).squeeze(2)
-            dlam = torch.cholesky_solve(rhs2.unsqueeze(2), Ls).squeeze(2)       # S dlam = c - J H^-1 rhs1
-            dx = -(Hir + torch.bmm(HiJt, dlam.unsqueeze(2)).squeeze(2))         # dx = -H^-1 (rhs1 + J^T dlam)
+            rhs2 = c.unsqueeze(2) - torch.bmm(Y.transpose(1, 2), y)
+            dlam = torch.cholesky_solve(rhs2, Ls)
+            dx = -torch.linalg.solve_triangular(Lh.transpose(1, 2), y + torch.bmm(Y, dlam), upper=True).squeeze(2)
+            dlam = dlam.squeeze(2)
             dzL = torch.where(hasL, mu_c / sL - zL - zL / sL * dx, torch.zeros_like(dx))
             dzU = torch.where(hasU, mu_c / sU - zU + zU / sU * dx, torch.zeros_like(dx))
             # fraction to the boundary
