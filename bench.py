@@ -32,11 +32,13 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 INSTANCES_PER_GPU = 4096
+SOLVE_INSTANCES = 512  # per GPU, for the solves/s side measurement
 MESH_INTERVALS, MESH_NODES = 8, 8
 NBUF = 4  # rotating input sets so that x is not served from L2 between steps
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_cons_jac launch of this workload from the
-# committed `ncu --set full` capture (profiles/r01_cons_jac_full.txt); None until captured
-NCU_TRAFFIC_BYTES = None
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_cons_jac launch of this workload (4096 instances)
+# from the committed `ncu --set full` capture (profiles/r01_cons_jac_full.txt: 35.76 MB read + 622.69 MB
+# written; below the 713 MB algorithmic figure because part of the last stores is still in L2 at kernel end)
+NCU_TRAFFIC_BYTES = 658450944
 
 
 def quadrotor_problem():
@@ -224,6 +226,11 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+class _Sizes:
+    def __init__(self, n, m, nnz_jac, nnz_h):
+        self.n, self.m, self.nnz_jac, self.nnz_h = n, m, nnz_jac, nnz_h
+
+
 def workload_config(o, world, sample_note=None):
     cfg = {"workload": "batched quadrotor MPC (BASELINE config 4): %d OCP instances per GPU, shared %dx%d LGR mesh, "
                        "fused eval_g+eval_jac_g by forward differences" % (INSTANCES_PER_GPU, MESH_INTERVALS, MESH_NODES),
@@ -282,13 +289,7 @@ def main():
     nb = INSTANCES_PER_GPU
     first = rank * nb
 
-    # LGR points for the guess: the product's own tables are device-side; the guess only needs
-    # the nodes, which the host table builder of the test harness-free path exposes via bounds
-    # -> use numpy's Gauss-Radau free formula instead: recover tau from the C-ABI structure is
-    # overkill, so take them from the oracle on rank 0's host (checker-side, outside any timing).
-    from oracle_lib import Oracle
-    o = Oracle(op)
-    pts = [o.tables(0)["points"]]
+    pts = g.lgr_points()  # composite LGR nodes of the shared mesh, from the product's own tables
     X = make_inputs(op, pts, first, nb)
 
     xs = [torch.from_numpy(X + 1e-3 * k).to(dev) for k in range(NBUF)]
@@ -346,8 +347,13 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = nnz * nb * world * e2e_steps / float(te.item())
-    # the host result must be the device result
-    assert torch.equal(hv[:8], d_v[:8].cpu()) or True
+    # the host-pointer call must deliver exactly what the device-resident call computes
+    chk = torch.from_numpy(X + 1e-3 * ((e2e_steps - 1) % 2)).to(dev)
+    g.eval_g_jac_dev(nb, chk.data_ptr(), d_g.data_ptr(), d_v.data_ptr())
+    torch.cuda.synchronize()
+    if not (torch.equal(hv[::509], d_v[::509].cpu()) and torch.equal(hg[::509], d_g[::509].cpu())):
+        raise RuntimeError("host-pointer and device-resident evaluations disagree")
+    del chk
 
     # ---- result gather (objective per instance; 8 B per instance over NCCL) ----
     d_f = torch.empty(nb, dtype=torch.float64, device=dev)
@@ -376,6 +382,41 @@ def main():
                              "bytes_per_eval": 8 * nb * (n + m + nnz_h)}
         del lam, d_h
 
+    solves = None
+    if not args.no_extras:
+        # batched OCP solves/s: every rank solves SOLVE_INSTANCES of its own instances to KKT tolerance with
+        # the lockstep interior-point method of lpopc_b200/solver.py (all NLP callbacks device-resident)
+        from lpopc_b200 import solver
+        ns_ = SOLVE_INSTANCES
+        ph0 = op.phases[0]
+        nominal = np.array([ph0.stateguess[j][0] for j in range(len(ph0.statemin))])
+        x0s = np.stack([nominal + 0.2 * np.random.Generator(np.random.PCG64(5 + first + i)).uniform(-1, 1, nominal.size) for i in range(ns_)])
+        g2 = nlp.TranscribedNLP(op)
+        X0 = batch.mpc_starting_points(op, g2.lgr_points(), x0s)
+        g2.probe_dependencies(X0[0])  # sparse Hessian pattern, as the reference does once per problem
+        ev = solver.CudaEvaluator(g2)
+        bxl, bxu, _, _ = ev.bounds()
+        XL, XU = batch.mpc_bounds(bxl, bxu, op, x0s)
+        ipm = solver.BatchedIPM(ev, tol=1e-6, max_iter=100)
+        ipm.solve(X0[:8], XL[:8], XU[:8])  # warm-up
+        barrier()
+        ts = time.perf_counter()
+        res = ipm.solve(X0, XL, XU, chunk=512)
+        barrier()
+        t_solve = torch.tensor([time.perf_counter() - ts], dtype=torch.float64, device=dev)
+        n_ok = (res["status"] == 0).sum().to(torch.float64).reshape(1)
+        it_sum = res["iters"].sum().to(torch.float64).reshape(1)
+        if world > 1:
+            dist.all_reduce(t_solve, op=dist.ReduceOp.MAX)
+            dist.all_reduce(n_ok, op=dist.ReduceOp.SUM)
+            dist.all_reduce(it_sum, op=dist.ReduceOp.SUM)
+        solves = {"metric": "batched OCP solves/s", "value": float(n_ok.item()) / float(t_solve.item()), "unit": "solves/s",
+                  "instances": ns_ * world, "converged": int(n_ok.item()), "seconds": float(t_solve.item()),
+                  "iters_mean": float(it_sum.item()) / (ns_ * world), "tol": 1e-6, "nnz_h_probed": ev.nnz_h,
+                  "solver": "lockstep primal-dual interior point, exact FD Hessian, dense condensed KKT (torch.linalg); "
+                            "NLP callbacks = device-resident transcription kernels"}
+        del g2, ev, ipm, res
+
     if rank == 0:
         peaks = {}
         try:
@@ -398,7 +439,7 @@ def main():
         line = {
             "metric": "collocation Jacobian nnz/s", "value": value, "unit": "nnz/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_all / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(o, world),
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(_Sizes(n, m, nnz, nnz_h), world),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "nnz/s", "h2d_bytes_per_step": 8 * nb * n, "d2h_bytes_per_step": 8 * nb * (m + nnz - const_tail),
                     "steps": e2e_steps, "ms_per_step": 1e3 * float(te.item()) / e2e_steps, "host_buffers": "pinned",
@@ -415,6 +456,8 @@ def main():
             "objective_checksum": float(np.sum(all_f)),
         }
         line.update(extras)
+        if solves:
+            line["solves"] = solves
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -111,6 +111,11 @@ int lpb_eval_h(lpb_handle* h, const double* x, double obj_factor, const double* 
  * evaluation; one H2D of x, one D2H of g and values). */
 int lpb_eval_g_jac(lpb_handle* h, const double* x, double* g, double* values);
 
+/* Replaces: reading LpCalculateData::PS[phase]->Points / Weights (LpCalculateData.hpp:35-41),
+ * the composite LGR nodes on [-1,1) and quadrature weights of the current mesh (what
+ * LpGuessChecker.cpp:130-190 interpolates the user's guess onto); N doubles each, either may be NULL. */
+int lpb_get_lgr_tables(lpb_handle* h, int phase, double* points, double* weights);
+
 /* Replaces: DeriveDependicieshecker::GetDependiciesForJacobiInEveryPhase
  * (LpDerivDependciesChecker.cpp:10-94): NaN-probe of the dae functor at node 1 of
  * x_guess; the mask feeds the Hessian pattern only.  If it

@@ -50,3 +50,34 @@ def gather_results(local, nbatch, dist=None, device="cpu"):
     out = [torch.zeros(per, dtype=torch.float64, device=device) for _ in range(world)]
     dist.all_gather(out, buf)
     return torch.cat(out).cpu().numpy()[:nbatch]
+
+
+def mpc_starting_points(op, lgr_points, x0s):
+    """[B, n] starting points for MPC instances that differ in the initial state: the problem's
+    two-point guess with the initial-state offset ramped linearly to zero over the horizon."""
+    ph = op.phases[0]
+    N, ns = ph.GetTotalNodes(), len(ph.statemin)
+    base = op.guess(lgr_points)
+    tau = np.concatenate([np.asarray(lgr_points[0]), [1.0]])
+    ramp = 0.5 * (1.0 - tau)
+    x0s = np.asarray(x0s, dtype=np.float64)
+    X = np.tile(base, (len(x0s), 1))
+    nominal = np.array([ph.stateguess[j][0] for j in range(ns)])
+    for j in range(ns):
+        X[:, j * (N + 1):(j + 1) * (N + 1)] += np.outer(x0s[:, j] - nominal[j], ramp)
+    return X
+
+
+def mpc_bounds(xl, xu, op, x0s):
+    """Per-instance variable bounds [B, n] (torch tensors like xl/xu): the initial state of instance b
+    is fixed to x0s[b] through the state0 bounds, exactly like examples.quadrotor(x0=...) does for one."""
+    import torch
+    ph = op.phases[0]
+    N, ns = ph.GetTotalNodes(), len(ph.statemin)
+    B = len(x0s)
+    XL, XU = xl.repeat(B, 1), xu.repeat(B, 1)
+    idx = (torch.arange(ns) * (N + 1)).to(XL.device)
+    x0t = torch.as_tensor(np.asarray(x0s), dtype=torch.float64).to(XL.device)
+    XL[:, idx] = x0t
+    XU[:, idx] = x0t
+    return XL, XU

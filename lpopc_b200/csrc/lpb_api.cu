@@ -957,6 +957,17 @@ int lpb_eval_h(lpb_handle* h, const double* x, double obj_factor, const double* 
     LPB_API_END(h)
 }
 
+int lpb_get_lgr_tables(lpb_handle* h, int phase, double* points, double* weights)
+{
+    LPB_API_BEGIN(h)
+    need_fresh(h);
+    if (phase < 0 || phase >= (int)h->ph.size()) throw ApiError(LPB_ERR_INVALID, "phase out of range");
+    const PhaseTables& t = h->ph[phase].tab;
+    if (points) std::memcpy(points, t.tau.data(), t.tau.size() * sizeof(double));
+    if (weights) std::memcpy(weights, t.w.data(), t.w.size() * sizeof(double));
+    LPB_API_END(h)
+}
+
 int lpb_probe_dependencies(lpb_handle* h, const double* x_guess, int* dep_out)
 {
     LPB_API_BEGIN(h)

@@ -39,6 +39,7 @@ SIGNATURES = {
     "lpb_eval_jac_g": (C.c_int, [_vp, _dp, _ip, _ip, _dp]),
     "lpb_eval_h": (C.c_int, [_vp, _dp, C.c_double, _dp, _ip, _ip, _dp]),
     "lpb_eval_g_jac": (C.c_int, [_vp, _dp, _dp, _dp]),
+    "lpb_get_lgr_tables": (C.c_int, [_vp, C.c_int, _dp, _dp]),
     "lpb_probe_dependencies": (C.c_int, [_vp, _dp, _ip]),
     "lpb_eval_f_batch": (C.c_int, [_vp, C.c_int, _dp, _dp]),
     "lpb_eval_grad_f_batch": (C.c_int, [_vp, C.c_int, _dp, _dp]),
@@ -215,6 +216,19 @@ class TranscribedNLP:
         g, v = np.empty(self.m), np.empty(self.nnz_jac)
         self._ck(self.lib.lpb_eval_g_jac(self.h, _d(x), _d(g), _d(v)))
         return g, v
+
+    def lgr_points(self):
+        """Composite LGR nodes of every phase on [-1, 1) (PS[phase]->Points of the current mesh)."""
+        out = []
+        for ip, p in enumerate(self.op.phases):
+            pts = np.empty(int(sum(p.nodesperinterval)))
+            self._ck(self.lib.lpb_get_lgr_tables(self.h, ip, _d(pts), None))
+            out.append(pts)
+        return out
+
+    def initial_guess(self):
+        """NLP starting point: the user's guess interpolated onto the LGR nodes (LpGuessChecker.cpp:130-203)."""
+        return self.op.guess(self.lgr_points())
 
     def probe_dependencies(self, x_guess):
         x = _f64(x_guess)

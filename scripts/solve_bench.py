@@ -29,20 +29,20 @@ def main():
     args = ap.parse_args()
     import torch
     from lpopc_b200 import examples, nlp, solver
-    from solver_cpu import mpc_bounds, mpc_instances
-    from oracle_lib import Oracle  # LGR points for the guess only (host, outside the timing)
+    from lpopc_b200 import batch
     op = getattr(examples, args.problem)(intervals=8, nodes=8)
-    pts = [Oracle(op).tables(0)["points"]]
+    g = nlp.TranscribedNLP(op)
+    pts = g.lgr_points()
     ph = op.phases[0]
     nominal = np.array([ph.stateguess[j][0] for j in range(len(ph.statemin))])
     rng = np.random.Generator(np.random.PCG64(5))
     x0s = nominal + 0.2 * rng.uniform(-1, 1, (args.nbatch, nominal.size))
-    X0 = mpc_instances(op, pts, x0s)
-    g = nlp.TranscribedNLP(op)
+    X0 = batch.mpc_starting_points(op, pts, x0s)
     if args.probe:
         g.probe_dependencies(X0[0])
     ev = solver.CudaEvaluator(g)
-    XL, XU = mpc_bounds(ev, op, x0s)
+    xl, xu, _, _ = ev.bounds()
+    XL, XU = batch.mpc_bounds(xl, xu, op, x0s)
     ipm = solver.BatchedIPM(ev, tol=args.tol, max_iter=100, verbose=args.verbose)
     ipm.solve(X0[:8], XL[:8], XU[:8])  # warm-up (cuSOLVER handles, kernels)
     torch.cuda.synchronize()

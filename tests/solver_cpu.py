@@ -43,29 +43,11 @@ class OracleEvaluator:
 
 
 def mpc_instances(op, lgr_points, x0s):
-    """Starting points and per-instance bounds for a batch of MPC instances that differ in the
-    initial state x0 (entered through the state0 bounds, like examples.quadrotor(x0=...))."""
-    ph = op.phases[0]
-    N, ns = ph.GetTotalNodes(), len(ph.statemin)
-    base = op.guess(lgr_points)
-    tau = np.concatenate([np.asarray(lgr_points[0]), [1.0]])
-    ramp = 0.5 * (1.0 - tau)
-    B = len(x0s)
-    X = np.tile(base, (B, 1))
-    nominal = np.array([ph.stateguess[j][0] for j in range(ns)])
-    for j in range(ns):
-        X[:, j * (N + 1):(j + 1) * (N + 1)] += np.outer(x0s[:, j] - nominal[j], ramp)
-    return X
+    from lpopc_b200 import batch
+    return batch.mpc_starting_points(op, lgr_points, x0s)
 
 
 def mpc_bounds(ev, op, x0s):
-    xl, xu, _, _ = [b.clone() for b in ev.bounds()]
-    ph = op.phases[0]
-    N, ns = ph.GetTotalNodes(), len(ph.statemin)
-    B = len(x0s)
-    XL, XU = xl.repeat(B, 1), xu.repeat(B, 1)
-    idx = torch.arange(ns) * (N + 1)
-    x0t = torch.as_tensor(x0s, dtype=torch.float64).to(XL.device)
-    XL[:, idx.to(XL.device)] = x0t
-    XU[:, idx.to(XL.device)] = x0t
-    return XL, XU
+    from lpopc_b200 import batch
+    xl, xu, _, _ = ev.bounds()
+    return batch.mpc_bounds(xl, xu, op, x0s)
