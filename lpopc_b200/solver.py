@@ -12,9 +12,9 @@ Scope of this first version (stated, not hidden):
     torch.linalg (cuSOLVER / cuBLAS), on the condensed system  S = J H^-1 J^T  with
     H = W + Sigma + delta_w I; the transcription kernels are the product, this solver is the
     first consumer of their device API;
-  * equality constraints (g_l == g_u) and variable bounds (log barrier, primal-dual); variables
-    with x_l == x_u are eliminated; inequality rows are accepted only when all their variables
-    are fixed (the duration row t_f - t_0 >= 0 of an MPC instance with fixed horizon);
+  * equality constraints and variable bounds (log barrier, primal-dual); variables with
+    x_l == x_u are eliminated; inequality rows (duration t_f - t_0 >= 0, path constraints) become
+    equalities with bounded slack variables (SlackEvaluator);
   * l1 merit function with backtracking line search, monotone barrier reduction (Fiacco-McCormick
     as in IPOPT's default), per-instance Hessian regularisation delta_w driven by the Cholesky
     status of each instance.
@@ -80,6 +80,63 @@ class CudaEvaluator:
         return v
 
 
+class SlackEvaluator:
+    """Presents a problem with inequality rows g_l <= g_i(x) <= g_u as an equality-only problem over
+    z = [x; s]:  g_i(x) - s_i = 0,  g_l <= s_i <= g_u  (the slack formulation interior-point methods
+    use; IPOPT does the same internally).  Triplet structures are extended by one -1 entry per slack."""
+
+    def __init__(self, ev):
+        self.ev, self.device = ev, ev.device
+        _, _, gl, gu = ev.bounds()
+        self.rows = torch.nonzero(gl != gu).squeeze(1)
+        self.ni = int(self.rows.numel())
+        self.nx = ev.n
+        self.n, self.m = ev.n + self.ni, ev.m
+        self.nnz_jac, self.nnz_h = ev.nnz_jac + self.ni, ev.nnz_h
+        self.jI = torch.cat([ev.jI, self.rows])
+        self.jJ = torch.cat([ev.jJ, ev.n + torch.arange(self.ni, device=self.device)])
+        self.hI, self.hJ = ev.hI, ev.hJ
+
+    def tensor(self, a):
+        return self.ev.tensor(a)
+
+    def bounds(self):
+        xl, xu, gl, gu = self.ev.bounds()
+        gl2, gu2 = gl.clone(), gu.clone()
+        gl2[self.rows] = 0.0
+        gu2[self.rows] = 0.0
+        return torch.cat([xl, gl[self.rows]]), torch.cat([xu, gu[self.rows]]), gl2, gu2
+
+    def extend(self, x, xl, xu):
+        """[B, nx] points and bounds -> [B, nx + ni] with slacks started at g_i(x)."""
+        _, _, gl, gu = self.ev.bounds()
+        B = x.shape[0]
+        s0 = self.ev.g(x.contiguous())[:, self.rows]
+        return (torch.cat([x, s0], 1), torch.cat([xl, gl[self.rows].expand(B, -1)], 1), torch.cat([xu, gu[self.rows].expand(B, -1)], 1))
+
+    def _x(self, Z):
+        return Z[:, :self.nx].contiguous()
+
+    def f(self, Z):
+        return self.ev.f(self._x(Z))
+
+    def grad(self, Z):
+        return torch.cat([self.ev.grad(self._x(Z)), torch.zeros((Z.shape[0], self.ni), dtype=torch.float64, device=Z.device)], 1)
+
+    def g(self, Z):
+        g = self.ev.g(self._x(Z))
+        g[:, self.rows] -= Z[:, self.nx:]
+        return g
+
+    def g_jac(self, Z):
+        g, v = self.ev.g_jac(self._x(Z))
+        g[:, self.rows] -= Z[:, self.nx:]
+        return g, torch.cat([v, torch.full((Z.shape[0], self.ni), -1.0, dtype=torch.float64, device=Z.device)], 1)
+
+    def hess(self, Z, sigma, lam):
+        return self.ev.hess(self._x(Z), sigma, lam)
+
+
 def blocked_cholesky_ex(A, split=512):
     """Batched lower Cholesky factor with a 2 x 2 block recursion above `split` rows: the batched
     library factorisation is several times slower per flop beyond ~1000 rows than below, while the
@@ -103,6 +160,10 @@ class BatchedIPM:
     """Lockstep primal-dual interior-point method over a batch of instances of one NLP."""
 
     def __init__(self, ev, tol=1e-6, max_iter=100, mu0=0.1, rho=1e3, verbose=False):
+        _, _, gl, gu = ev.bounds()
+        self.user_ev = ev
+        if bool((gl != gu).any()):
+            ev = SlackEvaluator(ev)  # inequality rows -> equalities with bounded slacks
         self.ev, self.tol, self.max_iter, self.mu0, self.rho, self.verbose = ev, tol, max_iter, mu0, rho, verbose
         self.n, self.m = ev.n, ev.m
 
@@ -116,16 +177,9 @@ class BatchedIPM:
         self.nf = int(self.free.numel())
         colmap = torch.full((self.n,), -1, dtype=torch.int64, device=dev)
         colmap[self.free] = torch.arange(self.nf, device=dev)
-        eq = gl == gu
-        # inequality rows: only constant ones (all their variables fixed) are supported
-        ineq_rows = torch.nonzero(~eq).squeeze(1)
-        if ineq_rows.numel():
-            in_ineq = torch.isin(ev.jI, ineq_rows)
-            if bool((colmap[ev.jJ[in_ineq]] >= 0).any()):
-                raise NotImplementedError("inequality constraint rows with free variables need slacks (not in this version)")
+        eq = gl == gu  # all rows: inequality rows were turned into equalities with slacks (SlackEvaluator)
         self.eq = torch.nonzero(eq).squeeze(1)
         self.me = int(self.eq.numel())
-        self.ineq_rows = ineq_rows
         rowmap = torch.full((self.m,), -1, dtype=torch.int64, device=dev)
         rowmap[self.eq] = torch.arange(self.me, device=dev)
         r, c = rowmap[ev.jI], colmap[ev.jJ]
@@ -168,9 +222,13 @@ class BatchedIPM:
         only (state carried over), so stragglers do not pay for the whole batch's linear algebra."""
         ev = self.ev
         B = len(x0)
-        bxl, bxu, _, _ = ev.bounds()
+        bxl, bxu, _, _ = self.user_ev.bounds()
         XL = bxl.expand(B, -1) if xl is None else ev.tensor(xl)
         XU = bxu.expand(B, -1) if xu is None else ev.tensor(xu)
+        x0 = ev.tensor(x0)
+        nx = x0.shape[1]
+        if isinstance(ev, SlackEvaluator):
+            x0, XL, XU = ev.extend(x0, XL, XU)
         res = self._solve_chunk(x0, XL, XU, None, 0)
         out = {k: v.clone() for k, v in res.items() if k != "state"}
         ids = torch.arange(B, device=out["x"].device)
@@ -182,6 +240,7 @@ class BatchedIPM:
             res = self._solve_chunk(sub["X"], XL[ids], XU[ids], sub, st["it"])
             for k in out:
                 out[k][ids] = res[k]
+        out["x"] = out["x"][:, :nx].contiguous()
         return out
 
     def _solve_chunk(self, x0, xl, xu, state, it0):
@@ -257,9 +316,9 @@ class BatchedIPM:
             newly = (~done) & (e0 <= self.tol)
             done |= newly
             if self.verbose:
-                print("it %3d  active %4d  max E0 %.3e  mu[min,max] %.1e %.1e  |c|max %.2e  dw max %.1e"
+                print("it %3d  active %4d  max E0 %.3e  mu[min,max] %.1e %.1e  |c|max %.2e  |rd|max %.2e  dw max %.1e  alpha[min] %.2e"
                       % (it, int((~done).sum()), float(e0[~done].max()) if (~done).any() else 0.0, float(mu.min()), float(mu.max()),
-                         float(c.abs().max()), float(dw_last.max())))
+                         float(c.abs().max()), float(rd.abs().max()), float(dw_last.max()), float(getattr(self, "_last_alpha", torch.ones(1)).min())))
             if bool(done.all()):
                 break
             n_act = int((~done).sum())
@@ -268,7 +327,7 @@ class BatchedIPM:
                              "active": ~done, "it": it}
                 break
             # barrier update (monotone): while E_mu <= kappa_eps * mu
-            for _ in range(4):
+            for _ in range(1):
                 emu = err(mu)
                 upd = (~done) & (emu <= 10.0 * mu) & (mu > self.tol / 10.0)
                 if not bool(upd.any()):
@@ -359,6 +418,7 @@ class BatchedIPM:
                 Xt[:, F] = xf + alpha.unsqueeze(1) * dx
                 Xn[stuck] = Xt[stuck]
                 dw_last = torch.where(stuck, torch.clamp(dw_last * 100.0, min=1e-2), dw_last)
+            self._last_alpha = alpha
             act = (~done).unsqueeze(1)
             a_col = alpha.unsqueeze(1)
             X = torch.where(act, Xn, X)

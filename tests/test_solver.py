@@ -38,12 +38,22 @@ def test_ipm_converges_on_cartpole_cpu():
     assert np.allclose(r1["obj"].numpy(), r2["obj"].numpy(), rtol=1e-7)
 
 
-def test_ipm_rejects_unsupported_inequalities():
-    op = examples.bryson_denham()  # free final time: the duration row has free variables
+def test_ipm_inequality_rows_become_slacks():
+    """Hypersensitive (reference example, Lpopc/example/hypersensitive): the duration row t_f - t_0 >= 0 is an
+    inequality row; it is carried as an equality with a bounded slack and the solve converges to the
+    KKT tolerance.  Free-final-time problems (Bryson-Denham, brachistochrone) are outside what this
+    first solver version converges on reliably -- see DESIGN.md."""
+    op = examples.hypersensitive(intervals=8, nodes=6)
     ev = OracleEvaluator(op)
+    ipm = solver.BatchedIPM(ev, tol=1e-7, max_iter=60)
+    assert isinstance(ipm.ev, solver.SlackEvaluator) and ipm.ev.ni == 1
     X0 = op.guess([ev.o.tables(0)["points"]])[None, :]
-    with pytest.raises(NotImplementedError):
-        solver.BatchedIPM(ev).solve(X0)
+    r = ipm.solve(X0)
+    assert int(r["status"][0]) == 0 and float(r["kkt_error"][0]) <= 1e-7
+    assert r["x"].shape[1] == ev.n
+    g = ev.g(r["x"])
+    _, _, gl, gu = ev.bounds()
+    assert bool(((g >= gl - 1e-6) & (g <= gu + 1e-6)).all())
 
 
 @pytest.mark.gpu
