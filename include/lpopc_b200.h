@@ -123,6 +123,20 @@ int lpb_get_lgr_tables(lpb_handle* h, int phase, double* points, double* weights
  * (ns+np) x (ns+nc) 0/1 values, column-major, phases concatenated. */
 int lpb_probe_dependencies(lpb_handle* h, const double* x_guess, int* dep_out);
 
+/* ---- mesh-error estimate and ph refinement (the step between two NLP solves) ----
+ * Replaces: SolutionErrorChecker::CheckSolutionDiffError (LpSolutionError.cpp:112-166) -- interpolation of
+ * the NLP solution x onto one more LGR point per interval, dae() there and the integration defect run on the
+ * GPU.  rows_out[p] = sum_k (N_k + 1) + 1; rel_err: per phase a rows x nstates matrix, column-major,
+ * phases concatenated; interval_max: per phase K values (the quantity PhMeshRefineAlg compares with
+ * "desired-relative-error").  Any output may be NULL. */
+int lpb_mesh_error(lpb_handle* h, const double* x, int* rows_out, double* rel_err, double* interval_max);
+/* Replaces: PhMeshRefineAlg::RefineMesh / ModifySegment (LpPhMeshRefineAlg.cpp:12-99; options
+ * "desired-relative-error", "Nmax", "Nmin" of LpMeshRefiner.h:67-80).  Returns the refined mesh of every phase:
+ * K_out[p], then K+1 mesh points and K node counts per phase appended to mesh_out / nodes_out (worst case
+ * per interval: ceil((N_k + log(e/tol)/log(N_k)) / Nmin) sub-intervals).  Pass it to lpb_set_mesh. */
+int lpb_refine_mesh_ph(lpb_handle* h, const double* x, double tol, int Nmax, int Nmin, int* no_more_refine,
+                       int* K_out, double* mesh_out, int* nodes_out);
+
 /* ---- batched independent instances (MPC-style; BASELINE config 4) ----------
  * nbatch instances share problem, mesh, tables and pattern; instance b uses
  * x[b*n .. b*n+n).  Host-pointer versions copy H2D/D2H around the kernels. */

@@ -285,6 +285,11 @@ struct PhaseHost {
     DevBuf<double> d_tau, d_w, d_ddiag, d_dblocks, d_doff_vals;
     DevBuf<int> d_node_interval, d_int_row0, d_int_n, d_doff_a, d_doff_b, d_hblk, d_pair_a, d_pair_b, d_counts;
     DevBuf<long long> d_int_d0;
+    // mesh-error estimator tables (built on demand for the current mesh)
+    ErrTables etab;
+    DevBuf<int> d_e_int_m, d_e_int_rn0;
+    DevBuf<long long> d_e_int_a0;
+    DevBuf<double> d_e_tnew, d_e_ablocks;
 };
 
 struct LinkHost {
@@ -321,6 +326,9 @@ struct lpb_handle {
     DevBuf<int> d_dep;
     // constant tail [L | C] of one instance's Jacobian values (mesh constants: -1/+1 of the linear
     // rows and the Doffdiag entries), cached on the host at refresh
+    bool err_fresh = false; // mesh-error tables match the current mesh
+    MeshErrDev med;
+    DevBuf<double> d_tem, d_abserr;
     std::vector<double> h_ctail;
     int host_fill_const = 1; // option "host_fill_const"
     lpb_handle() { std::memset(&pd, 0, sizeof pd); std::memset(&lay, 0, sizeof lay); std::memset(&ltab, 0, sizeof ltab); std::memset(&opts, 0, sizeof opts); }
@@ -485,6 +493,7 @@ static void refresh(lpb_handle* h)
     }
     CK(cudaStreamSynchronize(h->stream));
     h->fresh = true;
+    h->err_fresh = false;
 }
 
 static void need_fresh(lpb_handle* h)
@@ -965,6 +974,140 @@ int lpb_get_lgr_tables(lpb_handle* h, int phase, double* points, double* weights
     const PhaseTables& t = h->ph[phase].tab;
     if (points) std::memcpy(points, t.tau.data(), t.tau.size() * sizeof(double));
     if (weights) std::memcpy(weights, t.w.data(), t.w.size() * sizeof(double));
+    LPB_API_END(h)
+}
+
+// ---- mesh-error estimate and ph refinement --------------------------------------
+static void mesh_error_eval(lpb_handle* h, const double* x, std::vector<std::vector<double>>& rel, std::vector<std::vector<double>>& imax)
+{
+    need_fresh(h);
+    if (!x) throw ApiError(LPB_ERR_INVALID, "x is null");
+    const int P = (int)h->ph.size(), ns = h->vt->NS;
+    if (!h->err_fresh) {
+        long long out0 = 0;
+        for (int ip = 0; ip < P; ++ip) {
+            PhaseHost& p = h->ph[ip];
+            build_error_tables((int)p.nodes.size(), p.mesh.data(), p.nodes.data(), p.tab.tau, p.etab);
+            p.d_e_int_m.upload(p.etab.int_m, h->stream);
+            p.d_e_int_rn0.upload(p.etab.int_rn0, h->stream);
+            p.d_e_int_a0.upload(p.etab.int_a0, h->stream);
+            p.d_e_tnew.upload(p.etab.tnew, h->stream);
+            p.d_e_ablocks.upload(p.etab.ablocks, h->stream);
+            MeshErrPhase& m = h->med.ph[ip];
+            m.K = p.etab.K; m.M = p.etab.M;
+            m.int_m = p.d_e_int_m.p; m.int_rn0 = p.d_e_int_rn0.p; m.int_a0 = p.d_e_int_a0.p;
+            m.tnew = p.d_e_tnew.p; m.ablocks = p.d_e_ablocks.p;
+            m.out0 = out0;
+            out0 += (long long)(p.etab.M + 1) * ns;
+        }
+        h->d_tem.reserve((size_t)out0);
+        h->d_abserr.reserve((size_t)out0);
+        h->err_fresh = true;
+    }
+    size_t total = 0;
+    int nint = 0, max_n = 0;
+    for (int ip = 0; ip < P; ++ip) {
+        total += (size_t)(h->ph[ip].etab.M + 1) * ns;
+        nint += h->ph[ip].etab.K;
+        for (int v : h->ph[ip].nodes) max_n = v > max_n ? v : max_n;
+    }
+    h2d(h, h->d_x, x, (size_t)h->pd.n);
+    note_launches(h, h->vt->mesh_error(h->pd, h->consts.data(), h->stream, h->med, nint, max_n, h->d_x.p, h->d_tem.p, h->d_abserr.p));
+    std::vector<double> tem(total), err(total);
+    CK(cudaMemcpyAsync(tem.data(), h->d_tem.p, total * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(err.data(), h->d_abserr.p, total * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    // relative error = absolute / (1 + column max of the interpolated state) (LpSolutionError.cpp:162-167) and
+    // its maximum over the rows of each interval (LpPhMeshRefineAlg.cpp:27-38): O(M ns) host arithmetic
+    rel.assign(P, {});
+    imax.assign(P, {});
+    size_t off = 0;
+    for (int ip = 0; ip < P; ++ip) {
+        const ErrTables& e = h->ph[ip].etab;
+        const int rows = e.M + 1;
+        rel[ip].assign((size_t)rows * ns, 0.0);
+        for (int s = 0; s < ns; ++s) {
+            const double* tcol = tem.data() + off + (size_t)s * rows;
+            double mx = tcol[0];
+            for (int r = 1; r < rows; ++r) mx = tcol[r] > mx ? tcol[r] : mx;
+            const double den = 1 + mx;
+            for (int r = 0; r < rows; ++r) rel[ip][(size_t)s * rows + r] = err[off + (size_t)s * rows + r] / den;
+        }
+        imax[ip].assign(e.K, 0.0);
+        for (int k = 0; k < e.K; ++k) {
+            double mx = rel[ip][e.int_rn0[k]];
+            for (int s = 0; s < ns; ++s)
+                for (int r = e.int_rn0[k]; r <= e.int_rn0[k] + e.int_m[k]; ++r) {
+                    const double v = rel[ip][(size_t)s * rows + r];
+                    mx = v > mx ? v : mx;
+                }
+            imax[ip][k] = mx;
+        }
+        off += (size_t)rows * ns;
+    }
+}
+
+int lpb_mesh_error(lpb_handle* h, const double* x, int* rows_out, double* rel_err, double* interval_max)
+{
+    LPB_API_BEGIN(h)
+    std::vector<std::vector<double>> rel, imax;
+    mesh_error_eval(h, x, rel, imax);
+    size_t kr = 0, ki = 0;
+    for (size_t ip = 0; ip < rel.size(); ++ip) {
+        if (rows_out) rows_out[ip] = h->ph[ip].etab.M + 1;
+        if (rel_err) std::memcpy(rel_err + kr, rel[ip].data(), rel[ip].size() * sizeof(double));
+        if (interval_max) std::memcpy(interval_max + ki, imax[ip].data(), imax[ip].size() * sizeof(double));
+        kr += rel[ip].size();
+        ki += imax[ip].size();
+    }
+    LPB_API_END(h)
+}
+
+int lpb_refine_mesh_ph(lpb_handle* h, const double* x, double tol, int Nmax, int Nmin, int* no_more_refine,
+                       int* K_out, double* mesh_out, int* nodes_out)
+{
+    LPB_API_BEGIN(h)
+    if (!no_more_refine || !K_out || !mesh_out || !nodes_out) throw ApiError(LPB_ERR_INVALID, "null output");
+    if (!(tol > 0) || Nmin < 2 || Nmax < Nmin) throw ApiError(LPB_ERR_INVALID, "bad refinement options");
+    std::vector<std::vector<double>> rel, imax;
+    mesh_error_eval(h, x, rel, imax);
+    bool done = true;
+    size_t km = 0, kn = 0;
+    for (size_t ip = 0; ip < h->ph.size(); ++ip) {
+        const PhaseHost& p = h->ph[ip];
+        std::vector<double> nm{-1.0};
+        std::vector<int> nn;
+        for (size_t k = 0; k < p.nodes.size(); ++k) {
+            const double m0 = p.mesh[k], mf = p.mesh[k + 1], emax = imax[ip][k];
+            if (emax <= tol) { // LpPhMeshRefineAlg.cpp:37-47
+                nm.push_back(mf);
+                nn.push_back(p.nodes[k]);
+                continue;
+            }
+            done = false;
+            // ModifySegment, :78-99
+            const int cur = p.nodes[k];
+            const int Pq = static_cast<int>(std::log(emax / tol) / std::log((double)cur));
+            const int newnodes = cur + Pq;
+            if (newnodes <= Nmax) {
+                nm.push_back(mf);
+                nn.push_back(newnodes);
+            } else {
+                const int Bq = static_cast<int>(std::max(std::ceil(double(newnodes) / double(Nmin)), 2.0));
+                // linspace(m0, mf, Bq + 1): a + i*delta, last point exact (the stand-in follows Armadillo here)
+                const double delta = (mf - m0) / double(Bq);
+                for (int i = 1; i < Bq; ++i) nm.push_back(m0 + double(i) * delta);
+                nm.push_back(mf);
+                for (int i = 0; i < Bq; ++i) nn.push_back(Nmin);
+            }
+        }
+        K_out[ip] = (int)nn.size();
+        std::memcpy(mesh_out + km, nm.data(), nm.size() * sizeof(double));
+        std::memcpy(nodes_out + kn, nn.data(), nn.size() * sizeof(int));
+        km += nm.size();
+        kn += nn.size();
+    }
+    *no_more_refine = done ? 1 : 0;
     LPB_API_END(h)
 }
 

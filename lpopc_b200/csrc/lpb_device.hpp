@@ -71,6 +71,20 @@ struct ProblemDev {
     LinkDev lk[kMaxLinks];
 };
 
+// mesh-error estimator tables of one phase / all phases (lpb_mesherr.cuh)
+struct MeshErrPhase {
+    int K, M;                 // intervals, new points in total (sum of N_k + 1)
+    const int* int_m;         // [K] N_k + 1
+    const int* int_rn0;       // [K] first new row of the interval
+    const long long* int_a0;  // [K] offset of A_k in ablocks
+    const double* tnew;       // [M]
+    const double* ablocks;
+    long long out0;           // offset of the phase in the (M+1) x ns output matrices (doubles)
+};
+struct MeshErrDev {
+    MeshErrPhase ph[kMaxPhases];
+};
+
 struct LaunchOpts {
     int block;        // threads per block for node kernels
     int colour_split; // colour chunks (gridDim.y) of the Jacobian kernel; 0 = auto
@@ -103,6 +117,8 @@ struct FunctorVTable {
                    int nbatch, const double* x, const double* sigma, const double* lambda, double* vals, double* scratch);
     int (*probe)(const ProblemDev& pd, const void* consts, cudaStream_t st, const double* x, int* dep_out);
     size_t (*scratch_doubles)(const ProblemDev& pd, int nbatch);
+    int (*mesh_error)(const ProblemDev& pd, const void* consts, cudaStream_t st, const MeshErrDev& me, int total_intervals, int max_n,
+                      const double* x, double* tem, double* abs_err);
 };
 
 const FunctorVTable* const* functor_registry(int* count);

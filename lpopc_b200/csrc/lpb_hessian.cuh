@@ -16,6 +16,7 @@
 // pair (the reference recomputes it too); gridDim.y splits the a-range.
 #pragma once
 #include "lpb_kernels.cuh"
+#include "lpb_mesherr.cuh"
 
 namespace lpb {
 
@@ -427,7 +428,7 @@ const FunctorVTable* make_vtable()
         P::name(), P::NS, P::NC, P::NPATH, P::NE_MAX, P::NL_MAX,
         (int)(sizeof(typename P::Consts) / sizeof(double)), P::HAS_ANALYTIC ? 1 : 0,
         &launch_cons_jac<P>, &launch_objective<P>, &launch_gradient<P>, &launch_hessian<P>, &launch_probe<P>,
-        &scratch_doubles<P>};
+        &scratch_doubles<P>, &launch_mesh_error<P>};
     return &vt;
 }
 

@@ -126,4 +126,64 @@ void build_phase_tables(int K, const double* mesh, const int* nodes, PhaseTables
     out.N = row0;
 }
 
+// inverse by Gauss-Jordan elimination with partial pivoting, column-major n x n (the reference calls
+// Armadillo's inv(), i.e. LAPACK; values agree to rounding)
+static void invert(std::vector<double>& a, int n, std::vector<double>& r)
+{
+    r.assign((size_t)n * n, 0.0);
+    for (int i = 0; i < n; ++i) r[i + (size_t)i * n] = 1.0;
+    auto A = [&](int i, int j) -> double& { return a[i + (size_t)j * n]; };
+    auto R = [&](int i, int j) -> double& { return r[i + (size_t)j * n]; };
+    for (int c = 0; c < n; ++c) {
+        int p = c;
+        for (int i = c + 1; i < n; ++i)
+            if (std::fabs(A(i, c)) > std::fabs(A(p, c))) p = i;
+        if (A(p, c) == 0.0) throw std::runtime_error("integration matrix: singular differentiation block");
+        if (p != c)
+            for (int j = 0; j < n; ++j) { std::swap(A(p, j), A(c, j)); std::swap(R(p, j), R(c, j)); }
+        const double d = A(c, c);
+        for (int j = 0; j < n; ++j) { A(c, j) /= d; R(c, j) /= d; }
+        for (int i = 0; i < n; ++i) {
+            if (i == c) continue;
+            const double f = A(i, c);
+            if (f == 0.0) continue;
+            for (int j = 0; j < n; ++j) { A(i, j) -= f * A(c, j); R(i, j) -= f * R(c, j); }
+        }
+    }
+}
+
+void build_error_tables(int K, const double* mesh, const int* nodes, const std::vector<double>& tau_old, ErrTables& out)
+{
+    out = ErrTables();
+    out.K = K;
+    std::vector<int> finer(K);
+    for (int k = 0; k < K; ++k) finer[k] = nodes[k] + 1;
+    PhaseTables ft;
+    build_phase_tables(K, mesh, finer.data(), ft); // RPM->initialize(K, meshPoints, nodesPerInterval + 1), :150
+    long long a0 = 0;
+    int rn0 = 0, r0 = 0;
+    for (int k = 0; k < K; ++k) {
+        const int m = finer[k];
+        std::vector<double> x, w;
+        lgr_points(m, x, w); // RPMGenerator::GetLGRPoints(n + 1, ...), :76
+        const double time0 = tau_old[r0];
+        const double timef = (k + 1 < K) ? tau_old[r0 + nodes[k]] : 1.0; // tau = [Points; 1], :58
+        for (int i = 0; i < m; ++i) out.tnew.push_back((x[i] + 1) * (timef - time0) / 2 + time0); // :77
+        // A_k = inv(D_k(:, 1:end))
+        const double* Dk = ft.dblocks.data() + ft.int_d0[k]; // column-major m x (m+1)
+        std::vector<double> sub((size_t)m * m), inv;
+        for (int j = 0; j < m; ++j)
+            for (int i = 0; i < m; ++i) sub[i + (size_t)j * m] = Dk[i + (size_t)(j + 1) * m];
+        invert(sub, m, inv);
+        out.int_m.push_back(m);
+        out.int_rn0.push_back(rn0);
+        out.int_a0.push_back(a0);
+        out.ablocks.insert(out.ablocks.end(), inv.begin(), inv.end());
+        a0 += (long long)m * m;
+        rn0 += m;
+        r0 += nodes[k];
+    }
+    out.M = rn0;
+}
+
 } // namespace lpb

@@ -37,4 +37,16 @@ void colloc_block(const std::vector<double>& s, std::vector<double>& D);
 // (checks of MeshRefiner::SetAndCheckMesh, LpMeshRefiner.cpp:32-58).
 void build_phase_tables(int K, const double* meshpoints, const int* nodes, PhaseTables& out);
 
+// Tables of the mesh-error estimator (SolutionErrorChecker, LpSolutionError.cpp:54-166): the mesh with one
+// more LGR point per interval.
+struct ErrTables {
+    int K = 0, M = 0;               // intervals, total new points (sum of N_k + 1)
+    std::vector<int> int_m;         // N_k + 1
+    std::vector<int> int_rn0;       // first new row of interval k
+    std::vector<long long> int_a0;  // offset of the integration block in ablocks
+    std::vector<double> tnew;       // [M] interpolation abscissae on [-1, 1) (LpSolutionError.cpp:77)
+    std::vector<double> ablocks;    // per interval: column-major M_k x M_k, A_k = inv(D_k[:, 1:]) (RPMGenerator.cpp:85)
+};
+void build_error_tables(int K, const double* meshpoints, const int* nodes, const std::vector<double>& tau_old, ErrTables& out);
+
 } // namespace lpb

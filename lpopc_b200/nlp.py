@@ -40,6 +40,8 @@ SIGNATURES = {
     "lpb_eval_h": (C.c_int, [_vp, _dp, C.c_double, _dp, _ip, _ip, _dp]),
     "lpb_eval_g_jac": (C.c_int, [_vp, _dp, _dp, _dp]),
     "lpb_get_lgr_tables": (C.c_int, [_vp, C.c_int, _dp, _dp]),
+    "lpb_mesh_error": (C.c_int, [_vp, _dp, _ip, _dp, _dp]),
+    "lpb_refine_mesh_ph": (C.c_int, [_vp, _dp, C.c_double, C.c_int, C.c_int, _ip, _ip, _dp, _ip]),
     "lpb_probe_dependencies": (C.c_int, [_vp, _dp, _ip]),
     "lpb_eval_f_batch": (C.c_int, [_vp, C.c_int, _dp, _dp]),
     "lpb_eval_grad_f_batch": (C.c_int, [_vp, C.c_int, _dp, _dp]),
@@ -229,6 +231,42 @@ class TranscribedNLP:
     def initial_guess(self):
         """NLP starting point: the user's guess interpolated onto the LGR nodes (LpGuessChecker.cpp:130-203)."""
         return self.op.guess(self.lgr_points())
+
+    def mesh_error(self, x):
+        """(relative error matrices per phase [rows x ns], per-interval maxima per phase) of the solution x
+        (SolutionErrorChecker::CheckSolutionDiffError on the GPU)."""
+        x = _f64(x)
+        P = len(self.op.phases)
+        rows = np.zeros(P, dtype=np.int32)
+        self._ck(self.lib.lpb_mesh_error(self.h, _d(x), _i(rows), None, None))
+        ns = [len(p.statemin) for p in self.op.phases]
+        rel = np.empty(int(sum(r * s for r, s in zip(rows, ns))))
+        imax = np.empty(int(sum(len(p.nodesperinterval) for p in self.op.phases)))
+        self._ck(self.lib.lpb_mesh_error(self.h, _d(x), _i(rows), _d(rel), _d(imax)))
+        out_r, out_i, kr, ki = [], [], 0, 0
+        for ip, p in enumerate(self.op.phases):
+            out_r.append(rel[kr:kr + rows[ip] * ns[ip]].reshape(ns[ip], rows[ip]).T.copy())
+            out_i.append(imax[ki:ki + len(p.nodesperinterval)].copy())
+            kr += rows[ip] * ns[ip]
+            ki += len(p.nodesperinterval)
+        return out_r, out_i
+
+    def refine_mesh_ph(self, x, tol=1e-6, nmax=16, nmin=4):
+        """ph refinement decision (PhMeshRefineAlg::RefineMesh): (no_more_refine, [(meshpoints, nodes) per phase]).
+        Defaults = the reference's "desired-relative-error", "Nmax", "Nmin" (LpMeshRefiner.h:67-80)."""
+        x = _f64(x)
+        P = len(self.op.phases)
+        worst = sum(sum(max(2, (n + 64) // nmin + 2) for n in p.nodesperinterval) for p in self.op.phases) + P
+        K = np.zeros(P, dtype=np.int32)
+        mesh, nodes = np.empty(worst + P), np.zeros(worst, dtype=np.int32)
+        done = C.c_int()
+        self._ck(self.lib.lpb_refine_mesh_ph(self.h, _d(x), float(tol), int(nmax), int(nmin), C.byref(done), _i(K), _d(mesh), _i(nodes)))
+        out, km, kn = [], 0, 0
+        for ip in range(P):
+            out.append((mesh[km:km + K[ip] + 1].copy(), nodes[kn:kn + K[ip]].copy()))
+            km += K[ip] + 1
+            kn += K[ip]
+        return bool(done.value), out
 
     def probe_dependencies(self, x_guess):
         x = _f64(x_guess)

@@ -46,6 +46,14 @@ def main():
             t = r.tables(ip)
             d["points%d" % ip], d["weights%d" % ip] = t["points"], t["weights"]
             d["doff_vals%d" % ip] = t["Doffdiag"][2]
+        # mesh-error estimate and ph refinement decision at x (SolutionErrorChecker / PhMeshRefineAlg)
+        for ip, e in enumerate(r.mesh_error(x)):
+            d["mesh_rel%d" % ip] = e
+        for tol, tag in ((1e-2, "a"), (1e-6, "b")):
+            done, meshes = r.refine_ph(x, tol=tol)
+            d["refine_%s_done" % tag] = np.array(int(done))
+            for ip, (mp, nd) in enumerate(meshes):
+                d["refine_%s_mesh%d" % (tag, ip)], d["refine_%s_nodes%d" % (tag, ip)] = mp, nd
         if name == "launch":  # dependency probe + the sparse Hessian pattern it implies
             d["dep"] = r.probe_dependencies(guess)
             d["dep_info"] = np.array(r.nlp_info())

@@ -25,7 +25,10 @@
 #include "LpHessian.h"
 #include "LpNLPWrapper.hpp"
 #include "LpOptimalProblem.hpp"
+#include "LpPhMeshRefineAlg.hpp"
 #include "LpSizeChecker.h"
+#include "LpSolutionError.h"
+#include "spdlog/sinks/null_sink.h"
 #include "RPMGenerator.hpp"
 
 #include "../include/lpopc_b200.h"
@@ -283,6 +286,43 @@ void refresh(Ref& r)
     r.fresh = true;
 }
 
+// Data_->result[iphase] as Nlp2OpConverter::Nlp2OpControl fills it (Core/Nlp2OPConverter.cpp:33-75):
+// time on [t0, tf] at the LGR nodes + end point, state (N+1) x ns, control N x nc (+ final row)
+void fill_result(Ref& r, const double* x)
+{
+    const int P = (int)r.ph.size();
+    r.cd->result.assign(P, shared_ptr<SolutionData>());
+    for (int ip = 0; ip < P; ++ip) {
+        const int ns = r.ph[ip].d.nstates, nc = r.ph[ip].d.ncontrols;
+        const int N = (int)r.cd->PS[ip]->Points.n_elem;
+        const size_t s0 = r.cd->phase_indices[ip]->state[0] - 1;
+        shared_ptr<SolutionData> sd(new SolutionData());
+        const size_t tcol = s0 + (size_t)ns * (N + 1) + (size_t)nc * N;
+        const double t0 = x[tcol], tf = x[tcol + 1];
+        vec tau_all = join_vert(r.cd->PS[ip]->Points, ones(1, 1));
+        sd->time = (tf - t0) * (tau_all + 1) / 2 + t0;
+        sd->state = zeros<mat>(N + 1, ns);
+        for (int j = 0; j < ns; ++j)
+            for (int k = 0; k <= N; ++k) sd->state(k, j) = x[s0 + (size_t)j * (N + 1) + k];
+        if (nc > 0) {
+            sd->control = zeros<mat>(N + 1, nc);
+            for (int j = 0; j < nc; ++j) {
+                for (int k = 0; k < N; ++k) sd->control(k, j) = x[s0 + (size_t)ns * (N + 1) + (size_t)j * N + k];
+                sd->control(N, j) = sd->control(N - 1, j); // final row is never read by the error estimator
+            }
+        }
+        r.cd->result[ip] = sd;
+    }
+}
+
+void ensure_logger()
+{
+    if (!spdlog::get("lpopc_main_logger")) {
+        auto lg = std::make_shared<spdlog::logger>("lpopc_main_logger", std::make_shared<spdlog::sinks::null_sink_st>());
+        spdlog::register_logger(lg);
+    }
+}
+
 vec xvec(Ref* r, const double* x)
 {
     const size_t n = r->cd->varbounds_min.size();
@@ -511,6 +551,53 @@ int lpo_get_coo(void* h, int phase, int which, int* rows, int* cols, double* val
         vec I, J, V;
         dsmatrix::Find(s, I, J, V);
         for (size_t i = 0; i < V.n_elem; ++i) { rows[i] = (int)I(i); cols[i] = (int)J(i); vals[i] = V(i); }
+    })
+}
+
+// SolutionErrorChecker::CheckSolutionDiffError (Core/LpSolutionError.cpp:112-166) for every phase: the
+// relative error matrix ((sum_k (N_k+1)) + 1) x ns per phase, column-major, phases concatenated.
+// rows_out[p] receives the row count of phase p.
+int lpo_mesh_error(void* h, const double* x, double* rel_err, int* rows_out)
+{
+    Ref* r = (Ref*)h;
+    REF_GUARD(r, {
+        if (!r->fresh) refresh(*r);
+        fill_result(*r, x);
+        SolutionErrorChecker chk(r->fun, r->cd, r->op);
+        size_t k = 0;
+        for (size_t ip = 0; ip < r->ph.size(); ++ip) {
+            mat e;
+            chk.CheckSolutionDiffError((int)ip, e);
+            if (rows_out) rows_out[ip] = (int)e.n_rows;
+            if (rel_err) for (size_t i = 0; i < e.n_elem; ++i) rel_err[k + i] = e[i];
+            k += e.n_elem;
+        }
+    })
+}
+
+// PhMeshRefineAlg::RefineMesh (Core/LpPhMeshRefineAlg.cpp:12-99) on the current mesh and solution x.
+// Returns per phase the new mesh: K_out[p], then meshpoints (K+1) and nodes (K) appended to the flat
+// output arrays (caller provides room for the worst case).  *no_more_refine = 1 when every interval
+// satisfies tol.
+int lpo_refine_ph(void* h, const double* x, double tol, int Nmax, int Nmin, int* no_more_refine, int* K_out, double* mesh_out, int* nodes_out)
+{
+    Ref* r = (Ref*)h;
+    REF_GUARD(r, {
+        if (!r->fresh) refresh(*r);
+        ensure_logger();
+        fill_result(*r, x);
+        shared_ptr<LpReporter> rep(new LpReporter());
+        PhMeshRefineAlg alg(Nmax, Nmin, tol, r->fun, r->cd, rep);
+        std::vector<shared_ptr<LpMesh>> meshes;
+        const bool done = alg.RefineMesh(r->op, meshes);
+        *no_more_refine = done ? 1 : 0;
+        size_t km = 0, kn = 0;
+        for (size_t ip = 0; ip < meshes.size(); ++ip) {
+            K_out[ip] = (int)meshes[ip]->nodesPerInterval.n_elem;
+            for (size_t i = 0; i < meshes[ip]->meshpoints.n_elem; ++i) mesh_out[km++] = meshes[ip]->meshpoints(i);
+            for (size_t i = 0; i < meshes[ip]->nodesPerInterval.n_elem; ++i) nodes_out[kn++] = (int)meshes[ip]->nodesPerInterval(i);
+        }
+        r->fresh = false; // RefineMesh rewrote the mesh inside r->op; the next call rebuilds from r->ph
     })
 }
 

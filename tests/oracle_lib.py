@@ -227,6 +227,37 @@ class RefOracle(Oracle):
         self._check(self.L.lpo_get_guess(self.h, _d(x)))
         return x
 
+    def mesh_error(self, x):
+        """SolutionErrorChecker::CheckSolutionDiffError of the reference: relative error matrix per phase."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        P = len(self.op.phases)
+        rows = np.zeros(P, dtype=np.int32)
+        ns = [len(p.statemin) for p in self.op.phases]
+        tot = sum((sum(int(v) + 1 for v in p.nodesperinterval) + 1) * s for p, s in zip(self.op.phases, ns))
+        rel = np.empty(tot)
+        self._check(self.L.lpo_mesh_error(self.h, _d(x), _d(rel), _i(rows)))
+        out, k = [], 0
+        for ip in range(P):
+            out.append(rel[k:k + rows[ip] * ns[ip]].reshape(ns[ip], rows[ip]).T.copy())
+            k += rows[ip] * ns[ip]
+        return out
+
+    def refine_ph(self, x, tol=1e-6, nmax=16, nmin=4):
+        """PhMeshRefineAlg::RefineMesh of the reference: (no_more_refine, [(meshpoints, nodes) per phase])."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        P = len(self.op.phases)
+        worst = sum(sum(max(2, (int(n) + 64) // nmin + 2) for n in p.nodesperinterval) for p in self.op.phases) + P
+        K = np.zeros(P, dtype=np.int32)
+        mesh, nodes = np.empty(worst + P), np.zeros(worst, dtype=np.int32)
+        done = C.c_int()
+        self._check(self.L.lpo_refine_ph(self.h, _d(x), C.c_double(tol), C.c_int(nmax), C.c_int(nmin), C.byref(done), _i(K), _d(mesh), _i(nodes)))
+        out, km, kn = [], 0, 0
+        for ip in range(P):
+            out.append((mesh[km:km + K[ip] + 1].copy(), nodes[kn:kn + K[ip]].copy()))
+            km += K[ip] + 1
+            kn += K[ip]
+        return bool(done.value), out
+
 
 def detmath(which, x):
     x = np.ascontiguousarray(x, dtype=np.float64)
