@@ -1,0 +1,75 @@
+"""Adaptive mesh loop: solve -> mesh-error estimate -> ph refinement -> re-transcribe -> warm start.
+
+Mirrors the mesh loop of the reference's LpopcAlgorithm::SolveOptimalControlProblem
+(Lpopc/src/Core/LpLpopcAlgorithm.cpp:17-46: `SolveNlp; Nlp2OpControl; while(!RefineMesh()){ UpdateGrid;
+GetSizes; GetBounds; GetGuess; SolveNlp; Nlp2OpControl; }`).  Every new grid means new n, m, nnz and
+new index maps: `lpb_set_mesh` + `lpb_refresh` rebuild them on the GPU (north_star item 3); the error
+estimate between two solves runs on the GPU as well (`lpb_mesh_error`).  The outer
+NLP solver is lpopc_b200.solver.BatchedIPM (batch of one), standing in for IPOPT.
+
+Guess transfer between grids (N3, host side like the reference): the previous solution becomes the
+guess (Nlp2OPConverter.cpp:160-193) and is interpolated onto the new LGR nodes with a natural cubic
+spline (LpGuessChecker.cpp:130-190, 208-294).
+"""
+import numpy as np
+
+
+def transfer_guess(op, x, old_points, new_points):
+    """Previous solution x on the old mesh -> starting point on the new mesh (natural cubic spline in tau)."""
+    from scipy.interpolate import CubicSpline
+    out, off = [], 0
+    for ip, p in enumerate(op.phases):
+        ns, nc = len(p.statemin), len(p.controlmin)
+        N = len(old_points[ip])
+        tau_o = np.concatenate([old_points[ip], [1.0]])
+        tau_n = np.concatenate([new_points[ip], [1.0]])
+        for j in range(ns):
+            out.append(CubicSpline(tau_o, x[off + j * (N + 1): off + (j + 1) * (N + 1)], bc_type="natural")(tau_n))
+        c0 = off + ns * (N + 1)
+        for j in range(nc):
+            out.append(CubicSpline(tau_o[:-1], x[c0 + j * N: c0 + (j + 1) * N], bc_type="natural")(tau_n[:-1]))
+        t0 = c0 + nc * N
+        out.append(x[t0:t0 + 2])
+        off = t0 + 2
+    return np.concatenate(out)
+
+
+def solve_adaptive(op, make_nlp, make_evaluator, solver_cls, mesh_tol=1e-6, nmax=16, nmin=4, max_grids=10, ipm_tol=1e-6,
+                   max_iter=200, verbose=False):
+    """Runs the mesh loop on `op` (its phases' meshes are updated in place).
+
+    make_nlp(op) -> object with lgr_points(), initial_guess(), set_mesh(), refresh(), probe_dependencies(),
+    refine_mesh_ph() (lpopc_b200.nlp.TranscribedNLP on the GPU); make_evaluator(nlp) -> evaluator for
+    solver_cls (lpopc_b200.solver.CudaEvaluator / BatchedIPM).  Returns (x, history)."""
+    nlp = make_nlp(op)
+    x = nlp.initial_guess()
+    nlp.probe_dependencies(x)  # once per problem, like LpopcAlgorithm::GetDependecies
+    history = []
+    for grid in range(1, max_grids + 1):
+        ev = make_evaluator(nlp)
+        res = solver_cls(ev, tol=ipm_tol, max_iter=max_iter).solve(x[None, :])
+        x = res["x"][0].cpu().numpy()
+        done, meshes = nlp.refine_mesh_ph(x, tol=mesh_tol, nmax=nmax, nmin=nmin)
+        _, imax = nlp.mesh_error(x)
+        rec = {"grid": grid, "n": ev.n, "m": ev.m, "nnz_jac": ev.nnz_jac, "nnz_h": ev.nnz_h,
+               "nodes": [int(np.sum(p.nodesperinterval)) for p in op.phases], "intervals": [len(p.nodesperinterval) for p in op.phases],
+               "objective": float(res["obj"][0]), "status": int(res["status"][0]), "iters": int(res["iters"][0]),
+               "max_rel_error": float(max(v.max() for v in imax)), "mesh_satisfied": bool(done)}
+        history.append(rec)
+        if verbose:
+            print(rec)
+        if done or rec["status"] != 0:
+            break
+        if all(np.array_equal(mp, p.meshpoints) and np.array_equal(nd, p.nodesperinterval) for p, (mp, nd) in zip(op.phases, meshes)):
+            # PhMeshRefineAlg::ModifySegment truncates log(e/tol)/log(N) towards zero (LpPhMeshRefineAlg.cpp:81), so an
+            # interval whose error exceeds tol by less than a factor N is "refined" to itself; the reference would
+            # repeat the identical solve until max-grid-num -- stop instead and say so
+            rec["mesh_stalled"] = True
+            break
+        old_pts = nlp.lgr_points()
+        for ip, (mp, nd) in enumerate(meshes):
+            op.phases[ip].set_mesh(mp, nd)
+            nlp.set_mesh(ip, mp, nd)
+        nlp.refresh()  # new index maps / tables on the GPU
+        x = transfer_guess(op, x, old_pts, nlp.lgr_points())
+    return x, history

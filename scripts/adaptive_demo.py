@@ -1,0 +1,20 @@
+#!/usr/bin/env python
+"""Adaptive ph mesh refinement of the reference's hypersensitive example on the GPU: prints the grid history.
+    python scripts/adaptive_demo.py [tf] [mesh_tol]"""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from lpopc_b200 import adaptive, examples, nlp, solver  # noqa: E402
+
+tf = float(sys.argv[1]) if len(sys.argv) > 1 else 50.0
+tol = float(sys.argv[2]) if len(sys.argv) > 2 else 1e-5
+op = examples.hypersensitive(intervals=4, nodes=6)
+for p in op.phases:  # horizon override (the reference example uses 5000)
+    p.SetTimeMin(0.0, tf); p.SetTimeMax(0.0, tf)
+    p.timeguess = [0.0, tf]
+x, hist = adaptive.solve_adaptive(op, nlp.TranscribedNLP, solver.CudaEvaluator, solver.BatchedIPM, mesh_tol=tol, max_grids=12, verbose=False)
+for h in hist:
+    print(json.dumps(h))

@@ -1,0 +1,40 @@
+"""Adaptive mesh loop (lpopc_b200/adaptive.py): guess transfer on the CPU; the full loop -- solve, GPU mesh-error
+estimate, ph refinement, GPU re-transcription -- on the reference's hypersensitive example (-m gpu)."""
+import numpy as np
+import pytest
+
+from lpopc_b200 import adaptive, examples
+
+
+def test_transfer_guess_reproduces_smooth_profiles():
+    op = examples.bryson_denham(intervals=3, nodes=5)
+    rng = np.random.Generator(np.random.PCG64(1))
+    old = [np.sort(rng.uniform(-1, 1, 15))]
+    old[0][0] = -1.0
+    new = [np.sort(rng.uniform(-1, 1, 22))]
+    new[0][0] = -1.0
+    f = [lambda t: 1 + 0.5 * t, lambda t: np.sin(t), lambda t: t ** 2, lambda t: np.cos(2 * t)]
+    tau_o, tau_n = np.concatenate([old[0], [1.0]]), np.concatenate([new[0], [1.0]])
+    x = np.concatenate([f[0](tau_o), f[1](tau_o), f[2](tau_o), f[3](tau_o[:-1]), [0.0, 7.5]])
+    y = adaptive.transfer_guess(op, x, old, new)
+    assert y.size == 3 * 23 + 22 + 2 and np.array_equal(y[-2:], [0.0, 7.5])
+    assert np.allclose(y[:23], f[0](tau_n), atol=1e-12)          # linear profiles are reproduced exactly
+    assert np.allclose(y[23:46], f[1](tau_n), atol=2e-2)
+    assert np.allclose(y[69:91], f[3](tau_n[:-1]), atol=5e-2)
+
+
+@pytest.mark.gpu
+def test_adaptive_loop_hypersensitive_on_gpu():
+    from lpopc_b200 import nlp, solver
+    op = examples.hypersensitive(intervals=4, nodes=6)
+    for p in op.phases:  # a horizon the ph method resolves in a few grids (the reference example uses 5000)
+        p.SetTimeMin(0.0, 50.0); p.SetTimeMax(0.0, 50.0)
+        p.timeguess = [0.0, 50.0]
+    x, hist = adaptive.solve_adaptive(op, nlp.TranscribedNLP, solver.CudaEvaluator, solver.BatchedIPM, mesh_tol=1e-5, max_grids=12)
+    assert len(hist) >= 3 and all(h["status"] == 0 for h in hist)
+    # the loop ends on a satisfied mesh, or where the reference's truncated node increment stalls (see adaptive.py)
+    assert hist[-1]["mesh_satisfied"] or hist[-1].get("mesh_stalled")
+    assert hist[-1]["n"] > hist[0]["n"] and hist[-1]["max_rel_error"] <= 0.05 * hist[0]["max_rel_error"]
+    assert hist[-1]["max_rel_error"] <= 16e-5  # within the factor N_k <= Nmax of the tolerance that the truncation leaves
+    assert abs(hist[-1]["objective"] - 1.33077) <= 2e-3  # value the refined meshes converge to
+    assert x.size == hist[-1]["n"]
