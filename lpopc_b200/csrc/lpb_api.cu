@@ -331,6 +331,7 @@ struct lpb_handle {
     DevBuf<double> d_tem, d_abserr;
     std::vector<double> h_ctail;
     int host_fill_const = 1; // option "host_fill_const"
+    int host_threads = 0;    // option "host_threads": threads of the constant-tail fill (0 = min(hardware threads, 16))
     lpb_handle() { std::memset(&pd, 0, sizeof pd); std::memset(&lay, 0, sizeof lay); std::memset(&ltab, 0, sizeof ltab); std::memset(&opts, 0, sizeof opts); }
     ~lpb_handle()
     {
@@ -865,6 +866,7 @@ int lpb_eval_g_jac_batch(lpb_handle* h, int nbatch, const double* x, double* g, 
         unsigned hw = std::thread::hardware_concurrency();
         int nt = (int)(hw ? hw : 1);
         if (nt > 16) nt = 16;
+        if (h->host_threads > 0) nt = h->host_threads;
         if ((size_t)nbatch * tail < (size_t)1 << 16) nt = 1;
         if (nt > nbatch) nt = nbatch;
         const double* src = h->h_ctail.data();
@@ -1138,6 +1140,7 @@ int lpb_set_option_int(lpb_handle* h, const char* name, int value)
     else if (!std::strcmp(name, "pair_split")) h->opts.pair_split = value;
     else if (!std::strcmp(name, "block")) h->opts.block = value;
     else if (!std::strcmp(name, "host_fill_const")) h->host_fill_const = value;
+    else if (!std::strcmp(name, "host_threads")) h->host_threads = value;
     else if (!std::strcmp(name, "unroll_colours")) h->opts.unroll_colours = value;
     else if (!std::strcmp(name, "time_kernels")) h->time_kernels = value != 0;
     else throw ApiError(LPB_ERR_INVALID, std::string("unknown option ") + name);
