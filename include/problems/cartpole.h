@@ -9,6 +9,7 @@ struct LpbCartpole {
     static constexpr int NS = 4, NC = 1, NPATH = 0, NE_MAX = 0, NL_MAX = 0;
     static constexpr bool HAS_ANALYTIC = false;
     static constexpr bool UNROLL_COLOURS = true; /* compile-time colour unrolling of the FD Jacobian kernel */
+    static constexpr bool UNROLL_HESSIAN = UNROLL_COLOURS; /* pragma-unrolled pair loops of the Hessian kernel */
     struct Consts { double mc, mp, l, g, qx, qth, qv, ru; };
     static const char* name() { return "cartpole"; }
 

@@ -12,6 +12,7 @@ struct LpbLaunch {
     static constexpr int NS = 7, NC = 3, NPATH = 1, NE_MAX = 5, NL_MAX = 7;
     static constexpr bool HAS_ANALYTIC = false;
     static constexpr bool UNROLL_COLOURS = true; /* compile-time colour unrolling of the FD Jacobian kernel */
+    static constexpr bool UNROLL_HESSIAN = UNROLL_COLOURS; /* pragma-unrolled pair loops of the Hessian kernel */
     /* CONSTANTS of Launch.cpp:50-74,148-153 (omega = earthRotRate*scales.time) */
     struct Consts {
         double omega, mu, cd, sa, rho0, H, Re, g0;

@@ -11,6 +11,7 @@ struct LpbOrbitRaising {
     static constexpr int NS = 5, NC = 2, NPATH = 1, NE_MAX = 2, NL_MAX = 0;
     static constexpr bool HAS_ANALYTIC = false;
     static constexpr bool UNROLL_COLOURS = true; /* compile-time colour unrolling of the FD Jacobian kernel */
+    static constexpr bool UNROLL_HESSIAN = UNROLL_COLOURS; /* pragma-unrolled pair loops of the Hessian kernel */
     struct Consts { double T, mu, mdot; };
     static const char* name() { return "orbit_raising"; }
 

@@ -12,6 +12,7 @@ struct LpbQuadrotor {
     static constexpr int NS = 12, NC = 4, NPATH = 0, NE_MAX = 0, NL_MAX = 0;
     static constexpr bool HAS_ANALYTIC = false;
     static constexpr bool UNROLL_COLOURS = true; /* compile-time colour unrolling of the FD Jacobian kernel */
+    static constexpr bool UNROLL_HESSIAN = UNROLL_COLOURS; /* pragma-unrolled pair loops of the Hessian kernel */
     struct Consts {
         double mass, g, Ixx, Iyy, Izz, arm, kM;
         double qp, qv, qa, qw, ru;

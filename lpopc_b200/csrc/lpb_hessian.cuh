@@ -389,9 +389,9 @@ int launch_hessian(const ProblemDev& pd, const void* consts, cudaStream_t st, co
     // the unrolled variant is only instantiated for functor sets that ask for it (its code size and
     // compile time grow with the square of the variable count)
     bool unroll = false;
-    if constexpr (P::UNROLL_COLOURS) unroll = o.unroll_colours != 0;
+    if constexpr (P::UNROLL_HESSIAN) unroll = o.unroll_colours != 0;
     if (unroll) {
-        if constexpr (P::UNROLL_COLOURS)
+        if constexpr (P::UNROLL_HESSIAN)
             k_hess_nodes<P, true><<<dim3(gx, split), block, 0, st>>>(pd, C, nbatch, x, sigma, lambda, vals, scratch);
     } else
         k_hess_nodes<P, false><<<dim3(gx, split), block, 0, st>>>(pd, C, nbatch, x, sigma, lambda, vals, scratch);
