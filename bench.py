@@ -410,7 +410,7 @@ def main():
         ev = solver.CudaEvaluator(g2)
         bxl, bxu, _, _ = ev.bounds()
         XL, XU = batch.mpc_bounds(bxl, bxu, op, x0s)
-        ipm = solver.BatchedIPM(ev, tol=1e-6, max_iter=100)
+        ipm = solver.BatchedIPM(ev, tol=1e-6, max_iter=150)
         ipm.solve(X0[:8], XL[:8], XU[:8])  # warm-up
         barrier()
         ts = time.perf_counter()

@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--split", type=int, nargs="*", default=[0])
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--hessian", action="store_true")
+    ap.add_argument("--fg", action="store_true", help="also time eval_f and eval_grad_f")
     ap.add_argument("--pair-split", type=int, nargs="*", default=[0])
     args = ap.parse_args()
     import torch
@@ -72,6 +73,22 @@ def main():
             g.set_option("time_kernels", 0)
             print("unroll=%2d split=%2d  step %.4f ms (%.1f%% hbm, %.3e nnz/s)  k_cons_jac %.4f ms" %
                   (un, sp, ms, 100 * step_bytes / (ms * 1e-3) / 1e9 / peak, nnz * nb / (ms * 1e-3), kms / max(kc, 1)))
+    if args.fg:
+        d_f = torch.empty(nb, dtype=torch.float64, device="cuda")
+        d_gr = torch.empty((nb, n), dtype=torch.float64, device="cuda")
+        for name, fn, nbytes in (("eval_f", lambda k: g.eval_f_dev(nb, xs[k % 4].data_ptr(), d_f.data_ptr()), 8 * nb * (n + 1)),
+                                 ("eval_grad_f", lambda k: g.eval_grad_f_dev(nb, xs[k % 4].data_ptr(), d_gr.data_ptr()), 16 * nb * n)):
+            for k in range(3):
+                fn(k)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for k in range(args.steps):
+                fn(k)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / args.steps
+            print("%-12s %.4f ms (%.1f%% hbm on %d MB)" % (name, ms, 100 * nbytes / (ms * 1e-3) / 1e9 / peak, nbytes // 1000000))
     if args.hessian:
         lam = torch.from_numpy(rng.uniform(-1, 1, (nb, m))).cuda()
         sg = torch.ones(nb, dtype=torch.float64, device="cuda")
