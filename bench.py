@@ -32,7 +32,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 INSTANCES_PER_GPU = 4096
-SOLVE_INSTANCES = 512  # per GPU, for the solves/s side measurement
+SOLVE_INSTANCES = 4096  # per GPU, for the solves/s side measurement
 MESH_INTERVALS, MESH_NODES = 8, 8
 NBUF = 4  # rotating input sets so that x is not served from L2 between steps
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_cons_jac launch of this workload (4096 instances)
@@ -410,11 +410,11 @@ def main():
         ev = solver.CudaEvaluator(g2)
         bxl, bxu, _, _ = ev.bounds()
         XL, XU = batch.mpc_bounds(bxl, bxu, op, x0s)
-        ipm = solver.BatchedIPM(ev, tol=1e-6, max_iter=150)
+        ipm = solver.BatchedIPM(ev, tol=1e-6, max_iter=150, var_blocks=solver.interval_blocks(op, ev.n))
         ipm.solve(X0[:8], XL[:8], XU[:8])  # warm-up
         barrier()
         ts = time.perf_counter()
-        res = ipm.solve(X0, XL, XU, chunk=512)
+        res = ipm.solve(X0, XL, XU, chunk=SOLVE_INSTANCES)
         barrier()
         t_solve = torch.tensor([time.perf_counter() - ts], dtype=torch.float64, device=dev)
         n_ok = (res["status"] == 0).sum().to(torch.float64).reshape(1)
@@ -426,8 +426,8 @@ def main():
         solves = {"metric": "batched OCP solves/s", "value": float(n_ok.item()) / float(t_solve.item()), "unit": "solves/s",
                   "instances": ns_ * world, "converged": int(n_ok.item()), "seconds": float(t_solve.item()),
                   "iters_mean": float(it_sum.item()) / (ns_ * world), "tol": 1e-6, "nnz_h_probed": ev.nnz_h,
-                  "solver": "lockstep primal-dual interior point, exact FD Hessian, dense condensed KKT (torch.linalg); "
-                            "NLP callbacks = device-resident transcription kernels"}
+                  "solver": "lockstep primal-dual interior point, exact FD Hessian, KKT step: %s (torch.linalg batched Cholesky / "
+                            "triangular solves); NLP callbacks = device-resident transcription kernels" % ipm.kkt_kind}
         del g2, ev, ipm, res
 
     if rank == 0:

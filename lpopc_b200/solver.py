@@ -156,10 +156,293 @@ def blocked_cholesky_ex(A, split=512):
     return L, torch.where(i1 != 0, i1, i2)
 
 
+
+class DenseKKT:
+    """Condensed dense KKT step: S = J H^-1 J^T with H = W + Sigma + rho J^T J + dw I (library Cholesky)."""
+
+    def __init__(self, ipm):
+        self.ipm = ipm
+
+    def set_jac(self, jv):
+        self.J = self.ipm._dense_jac(jv)
+
+    def Jt(self, v):
+        return torch.bmm(self.J.transpose(1, 2), v.unsqueeze(2)).squeeze(2)
+
+    def step(self, hv, Sigma, rhs1, c, dw_last, done):
+        ipm, J = self.ipm, self.J
+        nf, me, rho = ipm.nf, ipm.me, ipm.rho
+        dev = J.device
+        W = ipm._dense_hess(hv)
+        # factor H_rho = W + Sigma + rho J^T J + dw I.  Adding rho J^T (J dx + c) = 0 to the first
+        # block row leaves (dx, dlam) unchanged, and by Debreu's lemma H_rho is positive definite for
+        # large rho exactly when the Hessian is positive definite on the null space of J -- the
+        # inertia condition an interior-point step needs -- so the Cholesky status of each instance
+        # drives its own regularisation dw (raised only for genuine negative curvature).
+        JtJ = torch.bmm(J.transpose(1, 2), J)
+        rhs1 = rhs1 + rho * self.Jt(c)
+        dw = torch.where(dw_last > 0, dw_last / 3.0, torch.zeros_like(dw_last))
+        dw = torch.where(dw < 1e-9, torch.zeros_like(dw), dw)
+        Hd = W + rho * JtJ
+        diag = torch.arange(nf, device=dev)
+        base_diag = Hd[:, diag, diag] + Sigma
+        for _try in range(40):
+            Hd[:, diag, diag] = base_diag + dw.unsqueeze(1)
+            Lh, info = blocked_cholesky_ex(Hd)
+            bad = (info != 0) & (~done)
+            if not bool(bad.any()):
+                break
+            dw = torch.where(bad, torch.where(dw == 0, torch.full_like(dw, 1e-4), dw * (100.0 if _try < 2 else 8.0)), dw)
+        # condensed system of [H J^T; J 0][dx; dlam] = -[rhs1; c] with H = L L^T:
+        #   Y = L^-1 J^T, y = L^-1 rhs1, S = Y^T Y, S dlam = c - Y^T y, dx = -L^-T (y + Y dlam)
+        Yr = torch.linalg.solve_triangular(Lh, torch.cat([J.transpose(1, 2), rhs1.unsqueeze(2)], dim=2), upper=False)
+        Y, y = Yr[:, :, :me], Yr[:, :, me:]
+        S = torch.bmm(Y.transpose(1, 2), Y)
+        dS = torch.arange(me, device=dev)
+        S[:, dS, dS] += 1e-12
+        Ls, info_s = blocked_cholesky_ex(S)
+        bad_s = (info_s != 0) & (~done)
+        failed = torch.zeros_like(done)
+        if bool(bad_s.any()):  # rank-deficient Jacobian: regularise the (2,2) block harder
+            S[:, dS, dS] += torch.where(bad_s, 1e-8, 0.0).unsqueeze(1)
+            Ls, info_s = blocked_cholesky_ex(S)
+            failed = (info_s != 0) & (~done)
+        rhs2 = c.unsqueeze(2) - torch.bmm(Y.transpose(1, 2), y)
+        dlam = torch.cholesky_solve(rhs2, Ls)
+        dx = -torch.linalg.solve_triangular(Lh.transpose(1, 2), y + torch.bmm(Y, dlam), upper=True).squeeze(2)
+        return dx, dlam.squeeze(2), dw, failed
+
+
+class BlockTridiagKKT:
+    """KKT step that exploits the mesh structure of the transcription.
+
+    With the free variables grouped by mesh interval (`var_blocks`), the Lagrangian Hessian couples only
+    variables of the same node and every constraint row touches at most two neighbouring intervals (the
+    defect rows of interval i read the first node of interval i+1), so H and J^T J are block tridiagonal
+    with blocks of about N_k (ns + nc) rows.  The step solves the dual-regularised system
+        [H  J^T; J  -delta I] [dx; dlam] = rhs,   delta = 1/gamma,
+    by eliminating dlam = gamma (J dx - rhs2):  (H + gamma J^T J) dx = rhs1 + gamma J^T rhs2  -- a block
+    tridiagonal positive definite system (batched block Cholesky, O(K nb^3) instead of O((K nb)^3)) -- and
+    removes the O(delta) regularisation error with a few steps of iterative refinement on the exact KKT
+    residual.  Positive definiteness of H + gamma J^T J is again the inertia test (Debreu), driving the
+    per-instance dw."""
+
+    def __init__(self, ipm, blk_free, gamma=1e6, refine=3):
+        self.ipm, self.gamma, self.refine = ipm, gamma, refine
+        ev, dev = ipm.ev, ipm.ev.device
+        nf, me = ipm.nf, ipm.me
+        K = int(blk_free.max().item()) + 1
+        self.K = K
+        # position of every free variable inside its block
+        order = torch.argsort(blk_free * nf + torch.arange(nf, device=dev))
+        counts = torch.bincount(blk_free, minlength=K)
+        starts = torch.cumsum(counts, 0) - counts
+        pos = torch.empty(nf, dtype=torch.int64, device=dev)
+        pos[order] = torch.arange(nf, device=dev) - starts[blk_free[order]]
+        nb = int(counts.max().item())
+        self.nb = nb
+        self.fpos = blk_free * nb + pos                      # free variable -> slot in the padded [K*nb] layout
+        # Jacobian rows: group = lowest block among the row's free columns
+        colmap = torch.full((ipm.n,), -1, dtype=torch.int64, device=dev)
+        colmap[ipm.free] = torch.arange(nf, device=dev)
+        rowmap = torch.full((ipm.m,), -1, dtype=torch.int64, device=dev)
+        rowmap[ipm.eq] = torch.arange(me, device=dev)
+        r, c = rowmap[ev.jI], colmap[ev.jJ]
+        sel = torch.nonzero((r >= 0) & (c >= 0)).squeeze(1)
+        rr, cb = r[sel], blk_free[c[sel]]
+        big = torch.full((me,), K, dtype=torch.int64, device=dev)
+        rmin = big.scatter_reduce(0, rr, cb, reduce="amin")
+        rmax = torch.full((me,), -1, dtype=torch.int64, device=dev).scatter_reduce(0, rr, cb, reduce="amax")
+        empty = rmax < 0
+        rmin = torch.where(empty, torch.zeros_like(rmin), rmin)
+        if bool(((rmax - rmin) > 1).any()):
+            raise ValueError("a constraint row couples non-adjacent blocks")
+        rorder = torch.argsort(rmin * me + torch.arange(me, device=dev))
+        rcounts = torch.bincount(rmin, minlength=K)
+        rstarts = torch.cumsum(rcounts, 0) - rcounts
+        rpos = torch.empty(me, dtype=torch.int64, device=dev)
+        rpos[rorder] = torch.arange(me, device=dev) - rstarts[rmin[rorder]]
+        mr = max(1, int(rcounts.max().item()))
+        self.mr = mr
+        self.dpos = rmin * mr + rpos                          # equality row -> slot in the padded [K*mr] layout
+        self.j_sel = sel
+        self.j_flat = (self.dpos[rr] * (2 * nb)) + (cb - rmin[rr]) * nb + pos[c[sel]]
+        # Hessian entries (lower triangle of the global matrix): same block -> D (both triangles), adjacent -> E
+        hr, hc = colmap[ev.hI], colmap[ev.hJ]
+        hs = torch.nonzero((hr >= 0) & (hc >= 0)).squeeze(1)
+        br, bc = blk_free[hr[hs]], blk_free[hc[hs]]
+        if bool(((br - bc).abs() > 1).any()):
+            raise ValueError("a Hessian entry couples non-adjacent blocks")
+        same = br == bc
+        pr, pc = pos[hr[hs]], pos[hc[hs]]
+        d1 = hs[same]
+        offd = same & (hr[hs] != hc[hs])
+        d2 = hs[offd]
+        self.hd_sel = torch.cat([d1, d2])
+        self.hd_flat = torch.cat([(br[same] * nb + pr[same]) * nb + pc[same], (br[offd] * nb + pc[offd]) * nb + pr[offd]])
+        adj = ~same
+        lo_is_c = br[adj] > bc[adj]   # row variable in the higher block
+        lo = torch.where(lo_is_c, bc[adj], br[adj])
+        p_hi = torch.where(lo_is_c, pr[adj], pc[adj])
+        p_lo = torch.where(lo_is_c, pc[adj], pr[adj])
+        self.he_sel = hs[adj]
+        self.he_flat = (lo * nb + p_hi) * nb + p_lo           # E[lo][p_hi][p_lo]: rows of block lo+1, cols of block lo
+        real = torch.zeros(K * nb, dtype=torch.bool, device=dev)
+        real[self.fpos] = True
+        self.pad_diag = (~real).to(torch.float64).view(K, nb)  # 1 on padded slots (keeps the blocks non-singular)
+
+    # layout conversions
+    def to_blocks(self, v):    # [B, nf] -> [B, K, nb]
+        out = torch.zeros((v.shape[0], self.K * self.nb), dtype=torch.float64, device=v.device)
+        out[:, self.fpos] = v
+        return out.view(-1, self.K, self.nb)
+
+    def from_blocks(self, vb):  # [B, K, nb] -> [B, nf]
+        return vb.reshape(vb.shape[0], -1)[:, self.fpos]
+
+    def dual_to_blocks(self, v):  # [B, me] -> [B, K, mr]
+        out = torch.zeros((v.shape[0], self.K * self.mr), dtype=torch.float64, device=v.device)
+        out[:, self.dpos] = v
+        return out.view(-1, self.K, self.mr)
+
+    def dual_from_blocks(self, vb):
+        return vb.reshape(vb.shape[0], -1)[:, self.dpos]
+
+    def set_jac(self, jv):
+        B = jv.shape[0]
+        Jb = torch.zeros((B, self.K * self.mr * 2 * self.nb), dtype=torch.float64, device=jv.device)
+        Jb.index_add_(1, self.j_flat, jv[:, self.j_sel])
+        self.Jb = Jb.view(B, self.K, self.mr, 2 * self.nb)
+
+    def _Jmul(self, xb):       # [B, K, nb] -> [B, K, mr]
+        nxt = torch.cat([xb[:, 1:], torch.zeros_like(xb[:, :1])], 1)
+        return torch.einsum("bkmn,bkn->bkm", self.Jb, torch.cat([xb, nxt], 2))
+
+    def _Jtmul(self, vb):      # [B, K, mr] -> [B, K, nb]
+        y = torch.einsum("bkmn,bkm->bkn", self.Jb, vb)
+        out = y[:, :, :self.nb].clone()
+        out[:, 1:] += y[:, :-1, self.nb:]
+        return out
+
+    def Jt(self, v):
+        return self.from_blocks(self._Jtmul(self.dual_to_blocks(v)))
+
+    def _Hmul(self, D, E, xb):
+        out = torch.einsum("bkij,bkj->bki", D, xb)
+        if self.K > 1:
+            out[:, 1:] += torch.einsum("bkij,bkj->bki", E, xb[:, :-1])
+            out[:, :-1] += torch.einsum("bkij,bki->bkj", E, xb[:, 1:])
+        return out
+
+    def _factor(self, Dp, Ep):
+        """Block-tridiagonal Cholesky: returns (list L_i, list C_i, info)."""
+        Ls, Cs = [], []
+        info = torch.zeros(Dp.shape[0], dtype=torch.int32, device=Dp.device)
+        eye = torch.eye(self.nb, dtype=torch.float64, device=Dp.device)
+        prev = None
+        for i in range(self.K):
+            A = Dp[:, i]
+            if i > 0:
+                C = torch.linalg.solve_triangular(prev, Ep[:, i - 1].transpose(1, 2), upper=False).transpose(1, 2)  # E L^-T
+                Cs.append(C)
+                A = A - torch.bmm(C, C.transpose(1, 2))
+            L, inf_i = torch.linalg.cholesky_ex(A)
+            bad = inf_i != 0
+            info = torch.where((info == 0) & bad, inf_i, info)
+            L = torch.where(bad.view(-1, 1, 1), eye.expand_as(L), L)  # keep failed instances finite
+            Ls.append(L)
+            prev = L
+        return Ls, Cs, info
+
+    def _solve(self, Ls, Cs, rb):
+        ys = []
+        for i in range(self.K):
+            t = rb[:, i]
+            if i > 0:
+                t = t - torch.bmm(Cs[i - 1], ys[-1].unsqueeze(2)).squeeze(2)
+            ys.append(torch.linalg.solve_triangular(Ls[i], t.unsqueeze(2), upper=False).squeeze(2))
+        xs = [None] * self.K
+        for i in range(self.K - 1, -1, -1):
+            t = ys[i]
+            if i + 1 < self.K:
+                t = t - torch.bmm(Cs[i].transpose(1, 2), xs[i + 1].unsqueeze(2)).squeeze(2)
+            xs[i] = torch.linalg.solve_triangular(Ls[i].transpose(1, 2), t.unsqueeze(2), upper=True).squeeze(2)
+        return torch.stack(xs, 1)
+
+    def step(self, hv, Sigma, rhs1, c, dw_last, done):
+        B, K, nb, g = hv.shape[0], self.K, self.nb, self.gamma
+        dev = hv.device
+        D = torch.zeros((B, K * nb * nb), dtype=torch.float64, device=dev)
+        D.index_add_(1, self.hd_flat, hv[:, self.hd_sel])
+        D = D.view(B, K, nb, nb)
+        E = torch.zeros((B, max(K - 1, 1) * nb * nb), dtype=torch.float64, device=dev)
+        if self.he_sel.numel():
+            E.index_add_(1, self.he_flat, hv[:, self.he_sel])
+        E = E.view(B, max(K - 1, 1), nb, nb)
+        di = torch.arange(nb, device=dev)
+        base = D[:, :, di, di] + self.to_blocks(Sigma) + self.pad_diag
+        G = torch.einsum("bkmi,bkmj->bkij", self.Jb, self.Jb)  # J_i^T J_i over the columns of blocks i and i+1
+        Dp = D + g * G[:, :, :nb, :nb]
+        if K > 1:
+            Dp[:, 1:] += g * G[:, :-1, nb:, nb:]
+            Ep = E + g * G[:, :-1, nb:, :nb]
+        else:
+            Ep = E
+        dw = torch.where(dw_last > 0, dw_last / 3.0, torch.zeros_like(dw_last))
+        dw = torch.where(dw < 1e-9, torch.zeros_like(dw), dw)
+        Gd = torch.diagonal(G, dim1=2, dim2=3)  # [B, K, 2 nb]
+        gdiag = g * (Gd[:, :, :nb] + torch.cat([torch.zeros_like(Gd[:, :1, nb:]), Gd[:, :-1, nb:]], 1))
+        for _try in range(40):
+            Dp[:, :, di, di] = base + gdiag + dw.view(-1, 1, 1)
+            Ls, Cs, info = self._factor(Dp, Ep)
+            bad = (info != 0) & (~done)
+            if not bool(bad.any()):
+                break
+            dw = torch.where(bad, torch.where(dw == 0, torch.full_like(dw, 1e-4), dw * (100.0 if _try < 2 else 8.0)), dw)
+        D[:, :, di, di] = base + dw.view(-1, 1, 1)  # H = W + Sigma + dw I (exact system of the refinement)
+        r1b, cb = self.to_blocks(rhs1), self.dual_to_blocks(c)
+        dxb = torch.zeros_like(r1b)
+        dlb = torch.zeros_like(cb)
+        for _ in range(1 + self.refine):
+            res1 = -r1b - (self._Hmul(D, E, dxb) + self._Jtmul(dlb))
+            res2 = -cb - self._Jmul(dxb)
+            ddx = self._solve(Ls, Cs, res1 + g * self._Jtmul(res2))
+            ddl = g * (self._Jmul(ddx) - res2)
+            dxb = dxb + ddx
+            dlb = dlb + ddl
+        failed = torch.zeros_like(done)
+        return self.from_blocks(dxb), self.dual_from_blocks(dlb), dw, failed
+
+
+def interval_blocks(op, n_total):
+    """Block id (mesh interval, phases concatenated) of every NLP variable of `op`; variables beyond the
+    transcription's own (slacks) and phase times get -1 (= decided from the rows they appear in)."""
+    blk = np.full(n_total, -1, dtype=np.int64)
+    off, b0 = 0, 0
+    for p in op.phases:
+        ns, nc = len(p.statemin), len(p.controlmin)
+        nodes = [int(v) for v in p.nodesperinterval]
+        N, K = sum(nodes), len(nodes)
+        node_blk = np.repeat(np.arange(K), nodes)
+        for j in range(ns):
+            blk[off + j * (N + 1): off + j * (N + 1) + N] = b0 + node_blk
+            blk[off + j * (N + 1) + N] = b0 + K - 1
+        c0 = off + ns * (N + 1)
+        for j in range(nc):
+            blk[c0 + j * N: c0 + (j + 1) * N] = b0 + node_blk
+        off = c0 + nc * N + 2
+        b0 += K
+    return blk
+
+
 class BatchedIPM:
     """Lockstep primal-dual interior-point method over a batch of instances of one NLP."""
 
-    def __init__(self, ev, tol=1e-6, max_iter=100, mu0=0.1, rho=1e3, verbose=False):
+    def __init__(self, ev, tol=1e-6, max_iter=100, mu0=0.1, rho=1e3, verbose=False, var_blocks=None):
+        """var_blocks: optional block id (mesh interval) per NLP variable (`interval_blocks(op, n)`): selects the
+        block-tridiagonal KKT step when the problem's coupling allows it, the dense condensed step otherwise."""
+        self.var_blocks = var_blocks
+        self.kkt_kind = "dense"
         _, _, gl, gu = ev.bounds()
         self.user_ev = ev
         if bool((gl != gu).any()):
@@ -191,6 +474,37 @@ class BatchedIPM:
         self.h_sel = torch.cat([sel, off])  # lower triangle + its mirror
         self.h_flat = torch.cat([hr[sel] * self.nf + hc[sel], hc[off] * self.nf + hr[off]])
         self.c_target = gl[self.eq]
+        self.kkt = DenseKKT(self)
+        self.kkt_kind = "dense"
+        if self.var_blocks is not None:
+            try:
+                self.kkt = BlockTridiagKKT(self, self._free_blocks())
+                self.kkt_kind = "block-tridiagonal (K=%d, nb=%d)" % (self.kkt.K, self.kkt.nb)
+            except ValueError:
+                pass  # coupling does not fit (free phase times, x0-xf Mayer terms, ...): dense step
+
+    def _free_blocks(self):
+        """Block id of every free variable: given ids where known, otherwise the lowest block among the variables
+        sharing a constraint row (slacks, which belong to the node of their row; isolated ones go to block 0)."""
+        ev, dev = self.ev, self.ev.device
+        vb = torch.as_tensor(np.asarray(self.var_blocks), dtype=torch.int64, device=dev)
+        blk = torch.full((self.n,), -1, dtype=torch.int64, device=dev)
+        blk[: vb.numel()] = vb
+        free_mask = torch.zeros(self.n, dtype=torch.bool, device=dev)
+        free_mask[self.free] = True
+        unknown = torch.nonzero((blk < 0) & free_mask).squeeze(1)
+        if unknown.numel():
+            big = int(blk.max().item()) + 1
+            known = (blk[ev.jJ] >= 0) & free_mask[ev.jJ]
+            rowmin = torch.full((self.m,), big, dtype=torch.int64, device=dev).scatter_reduce(0, ev.jI[known], blk[ev.jJ[known]], reduce="amin")
+            for v in unknown.tolist():
+                rows = ev.jI[ev.jJ == v]
+                b = int(rowmin[rows].min().item()) if rows.numel() else big
+                blk[v] = 0 if b >= big else b
+        out = blk[self.free]
+        if bool((out < 0).any()):
+            raise ValueError("free variable without a block")
+        return out
 
     def _dense_jac(self, vals):
         B = vals.shape[0]
@@ -294,11 +608,13 @@ class BatchedIPM:
             g, jv = ev.g_jac(X)
             gradf = ev.grad(X)[:, F]
             c = g[:, self.eq] - self.c_target
-            J = self._dense_jac(jv)
+            kkt = self.kkt
+            kkt.set_jac(jv)
             xf = X[:, F]
             sL, sU = sl(xf), su(xf)
             lam_eq = lam[:, self.eq]
-            rd = gradf + torch.bmm(J.transpose(1, 2), lam_eq.unsqueeze(2)).squeeze(2) - zL + zU
+            Jtlam = kkt.Jt(lam_eq)
+            rd = gradf + Jtlam - zL + zU
             compL = torch.where(hasL, sL * zL, torch.zeros_like(sL))
             compU = torch.where(hasU, sU * zU, torch.zeros_like(sU))
             # scaled optimality error (IPOPT eq. (5)-(6)), smax = 100
@@ -335,48 +651,12 @@ class BatchedIPM:
                 mu = torch.where(upd, torch.clamp(torch.minimum(0.2 * mu, mu ** 1.5), min=self.tol / 10.0), mu)
             mu_c = mu.unsqueeze(1)
             # Hessian of the Lagrangian (exact, finite differences of the reference scheme) + Sigma
-            W = self._dense_hess(ev.hess(X, sigma1, lam))
+            hv = ev.hess(X, sigma1, lam)
             Sigma = torch.where(hasL, zL / sL, torch.zeros_like(sL)) + torch.where(hasU, zU / sU, torch.zeros_like(sU))
-            rhs1 = gradf + torch.bmm(J.transpose(1, 2), lam_eq.unsqueeze(2)).squeeze(2) \
-                - torch.where(hasL, mu_c / sL, torch.zeros_like(sL)) + torch.where(hasU, mu_c / sU, torch.zeros_like(sU))
-            # factor H_rho = W + Sigma + rho J^T J + dw I.  Adding rho J^T (J dx + c) = 0 to the first
-            # block row leaves (dx, dlam) unchanged, and by Debreu's lemma H_rho is positive definite for
-            # large rho exactly when the Hessian is positive definite on the null space of J -- the
-            # inertia condition an interior-point step needs -- so the Cholesky status of each instance
-            # drives its own regularisation dw (raised only for genuine negative curvature).
-            rho = self.rho
-            JtJ = torch.bmm(J.transpose(1, 2), J)
-            rhs1 = rhs1 + rho * torch.bmm(J.transpose(1, 2), c.unsqueeze(2)).squeeze(2)
-            dw = torch.where(dw_last > 0, dw_last / 3.0, torch.zeros_like(dw_last))
-            dw = torch.where(dw < 1e-9, torch.zeros_like(dw), dw)
-            Hd = W + rho * JtJ
-            diag = torch.arange(nf, device=X.device)
-            base_diag = Hd[:, diag, diag] + Sigma
-            for _try in range(40):
-                Hd[:, diag, diag] = base_diag + dw.unsqueeze(1)
-                Lh, info = blocked_cholesky_ex(Hd)
-                bad = (info != 0) & (~done)
-                if not bool(bad.any()):
-                    break
-                dw = torch.where(bad, torch.where(dw == 0, torch.full_like(dw, 1e-4), dw * (100.0 if _try < 2 else 8.0)), dw)
+            rhs1 = gradf + Jtlam - torch.where(hasL, mu_c / sL, torch.zeros_like(sL)) + torch.where(hasU, mu_c / sU, torch.zeros_like(sU))
+            dx, dlam, dw, kfail = kkt.step(hv, Sigma, rhs1, c, dw_last, done)
+            failed |= kfail
             dw_last = torch.where(done, dw_last, dw)
-            # condensed system of [H J^T; J 0][dx; dlam] = -[rhs1; c] with H = L L^T:
-            #   Y = L^-1 J^T, y = L^-1 rhs1, S = Y^T Y, S dlam = c - Y^T y, dx = -L^-T (y + Y dlam)
-            Yr = torch.linalg.solve_triangular(Lh, torch.cat([J.transpose(1, 2), rhs1.unsqueeze(2)], dim=2), upper=False)
-            Y, y = Yr[:, :, :me], Yr[:, :, me:]
-            S = torch.bmm(Y.transpose(1, 2), Y)
-            dS = torch.arange(me, device=X.device)
-            S[:, dS, dS] += 1e-12
-            Ls, info_s = blocked_cholesky_ex(S)
-            bad_s = (info_s != 0) & (~done)
-            if bool(bad_s.any()):  # rank-deficient Jacobian: regularise the (2,2) block harder
-                S[:, dS, dS] += torch.where(bad_s, 1e-8, 0.0).unsqueeze(1)
-                Ls, info_s = blocked_cholesky_ex(S)
-                failed |= (info_s != 0) & (~done)
-            rhs2 = c.unsqueeze(2) - torch.bmm(Y.transpose(1, 2), y)
-            dlam = torch.cholesky_solve(rhs2, Ls)
-            dx = -torch.linalg.solve_triangular(Lh.transpose(1, 2), y + torch.bmm(Y, dlam), upper=True).squeeze(2)
-            dlam = dlam.squeeze(2)
             dzL = torch.where(hasL, mu_c / sL - zL - zL / sL * dx, torch.zeros_like(dx))
             dzU = torch.where(hasU, mu_c / sU - zU + zU / sU * dx, torch.zeros_like(dx))
             # fraction to the boundary

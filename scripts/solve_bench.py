@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--tol", type=float, default=1e-6)
     ap.add_argument("--probe", type=int, default=1, help="run the NaN dependency probe first (sparser Hessian pattern), like the reference")
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--dense", action="store_true", help="dense condensed KKT step instead of the block-tridiagonal one")
     args = ap.parse_args()
     import torch
     from lpopc_b200 import examples, nlp, solver
@@ -43,7 +44,8 @@ def main():
     ev = solver.CudaEvaluator(g)
     xl, xu, _, _ = ev.bounds()
     XL, XU = batch.mpc_bounds(xl, xu, op, x0s)
-    ipm = solver.BatchedIPM(ev, tol=args.tol, max_iter=100, verbose=args.verbose)
+    ipm = solver.BatchedIPM(ev, tol=args.tol, max_iter=150, verbose=args.verbose,
+                            var_blocks=None if args.dense else solver.interval_blocks(op, ev.n))
     ipm.solve(X0[:8], XL[:8], XU[:8])  # warm-up (cuSOLVER handles, kernels)
     torch.cuda.synchronize()
     l0, t0 = g.kernel_launches, time.perf_counter()
@@ -55,7 +57,7 @@ def main():
                       "converged": ok, "seconds": dt, "iters_mean": float(r["iters"].double().mean().item()), "iters_max": int(r["iters"].max().item()),
                       "kkt_error_max": float(r["kkt_error"].max().item()), "objective_mean": float(r["obj"].mean().item()),
                       "n": ev.n, "m": ev.m, "nnz_jac": ev.nnz_jac, "nnz_h": ev.nnz_h, "transcription_kernel_launches": g.kernel_launches - l0,
-                      "tol": args.tol, "chunk": args.chunk, "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9}))
+                      "tol": args.tol, "chunk": args.chunk, "kkt": ipm.kkt_kind, "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9}))
 
 
 if __name__ == "__main__":

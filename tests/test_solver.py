@@ -38,6 +38,24 @@ def test_ipm_converges_on_cartpole_cpu():
     assert np.allclose(r1["obj"].numpy(), r2["obj"].numpy(), rtol=1e-7)
 
 
+def test_block_tridiagonal_kkt_matches_dense_cpu():
+    op = examples.cartpole(intervals=4, nodes=5)
+    ev = OracleEvaluator(op)
+    x0s, X0 = _instances(op, ev, 3, 0.2, 1)
+    XL, XU = mpc_bounds(ev, op, x0s)
+    rd = solver.BatchedIPM(ev, tol=1e-7, max_iter=60).solve(X0, XL, XU)
+    ipm = solver.BatchedIPM(ev, tol=1e-7, max_iter=60, var_blocks=solver.interval_blocks(op, ev.n))
+    rb = ipm.solve(X0, XL, XU)
+    assert ipm.kkt_kind.startswith("block-tridiagonal")
+    assert int(rb["status"].abs().sum()) == 0 and np.allclose(rb["obj"].numpy(), rd["obj"].numpy(), rtol=1e-9)
+    # a problem whose coupling does not fit (free final time couples every node) falls back to the dense step
+    op2 = examples.bryson_denham(intervals=4, nodes=4)
+    ev2 = OracleEvaluator(op2)
+    ipm2 = solver.BatchedIPM(ev2, max_iter=1, var_blocks=solver.interval_blocks(op2, ev2.n))
+    ipm2.solve(op2.guess([ev2.o.tables(0)["points"]])[None, :])
+    assert ipm2.kkt_kind == "dense"
+
+
 def test_ipm_inequality_rows_become_slacks():
     """Hypersensitive (reference example, Lpopc/example/hypersensitive): the duration row t_f - t_0 >= 0 is an
     inequality row; it is carried as an equality with a bounded slack and the solve converges to the
@@ -70,6 +88,11 @@ def test_gpu_solves_match_cpu_reference_objectives(problem, kw, nb, spread):
     rg = solver.BatchedIPM(ev_gpu, tol=1e-7, max_iter=80).solve(X0, XL, XU)
     assert g.kernel_launches > l0
     assert int(rg["status"].abs().sum().item()) == 0
+    # block-tridiagonal KKT step (mesh structure) against the dense condensed step
+    ipm_b = solver.BatchedIPM(ev_gpu, tol=1e-7, max_iter=80, var_blocks=solver.interval_blocks(op, ev_gpu.n))
+    rb = ipm_b.solve(X0, XL, XU)
+    assert ipm_b.kkt_kind.startswith("block-tridiagonal") and int(rb["status"].abs().sum().item()) == 0
+    assert float(((rb["obj"] - rg["obj"]).abs() / rg["obj"].abs().clamp(min=1.0)).max().item()) <= 1e-8
     sample = [0, 1, nb - 1]
     XLc, XUc = mpc_bounds(ev_cpu, op, x0s[sample])
     rc = solver.BatchedIPM(ev_cpu, tol=1e-7, max_iter=80).solve(X0[sample], XLc, XUc)
