@@ -14,7 +14,7 @@ g.probe_dependencies(X0[0])
 ev = solver.CudaEvaluator(g)
 xl, xu, _, _ = ev.bounds()
 XL, XU = batch.mpc_bounds(xl, xu, op, x0s)
-ipm = solver.BatchedIPM(ev, tol=1e-6, max_iter=100)
+ipm = solver.BatchedIPM(ev, tol=1e-6, max_iter=100, var_blocks=solver.interval_blocks(op, ev.n))
 ipm.solve(X0[:8], XL[:8], XU[:8])
 torch.cuda.synchronize()
 from torch.profiler import profile, ProfilerActivity
