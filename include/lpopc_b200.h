@@ -143,6 +143,13 @@ int lpb_refine_mesh_ph(lpb_handle* h, const double* x, double tol, int Nmax, int
 int lpb_eval_f_batch(lpb_handle* h, int nbatch, const double* x, double* obj_values);
 int lpb_eval_grad_f_batch(lpb_handle* h, int nbatch, const double* x, double* grad_f);
 int lpb_eval_g_jac_batch(lpb_handle* h, int nbatch, const double* x, double* g, double* values);
+/* lpb_eval_g_jac_batch moves as few bytes over PCIe as the result allows: the mesh-constant tail [L | C]
+ * of the values is written by host threads from a cached copy, and -- when `values` is pinned host memory
+ * and the batch is large -- only the (row block, column block) segments of [NL] that have ever been
+ * non-zero are sent by the GPU (zero-copy stores); the all-zero segments of the reference's forced-dense
+ * pattern are verified on the device on every call and written as zeros by the host threads (a segment
+ * that turns non-zero is fetched afterwards, so the caller always gets the exact device values).
+ * Options "sparse_return" (default 1), "host_fill_const" (1), "host_threads" (0 = auto). */
 int lpb_eval_h_batch(lpb_handle* h, int nbatch, const double* x, const double* obj_factor,
                      const double* lambda, double* values);
 
@@ -161,6 +168,10 @@ int lpb_structure_dev(lpb_handle* h, const int** d_jac_iRow, const int** d_jac_j
 /* Tuning / introspection (not part of the reference boundary). */
 int lpb_set_option_int(lpb_handle* h, const char* name, int value);
 long long lpb_kernel_launch_count(const lpb_handle* h); /* kernels launched so far */
+/* Counters: "sparse_calls" (host-pointer calls that used the sparse return), "sparse_fixups" (segments fetched
+ * after a wrong all-zero prediction), "sparse_on_doubles" (values per instance that cross PCIe on that path),
+ * "head_doubles" (size of [NL] per instance). */
+int lpb_get_stat(lpb_handle* h, const char* name, long long* value);
 /* With option "time_kernels" = 1 every evaluation brackets its dominant node kernel
  * ("cons_jac": k_cons_jac, "hess_nodes": k_hess_nodes) with CUDA events on the handle's
  * stream; this returns and resets the accumulated device time and launch count. */

@@ -228,6 +228,56 @@ int launch_fill_const(const ProblemDev& pd, cudaStream_t st, int nbatch, double*
     return launches;
 }
 
+// ---- sparse return of the Jacobian head [NL] to a host array ---------------------------------
+// The host-pointer batch call is PCIe-bound, and for functor sets with sparse dependencies most
+// (row block, column block) segments of the head hold the same signed zero in every instance: the
+// reference forces the dense pattern (LpNLPWrapper.cpp:1106-1312), a structurally absent
+// derivative is the quotient +0.0 and the defect rows store its negation -0.0 (:712).  These
+// zeros are part of the contract but need not cross PCIe.  A segment is "off" while every value
+// it has ever held was one fill pattern (+0.0 or -0.0): a warp copies an ON segment of one
+// instance straight into the caller's pinned array (zero-copy stores over PCIe, 256-byte runs);
+// OFF segments are only CHECKED against their fill pattern and written by host threads.  A
+// mismatch raises flags[seg], and the host then fetches that segment from the device copy, so
+// the delivered values are always exactly the device values bit for bit, never a prediction.
+struct SegDev {
+    const int* off;            // [nseg] offset inside one instance's values
+    const int* len;            // [nseg]
+    const unsigned char* on;   // [nseg] 1: copy to the host, 0: verify against fill
+    const long long* fill;     // [nseg] bit pattern of an off segment
+    int* flags;                // [nseg] sparse mode: 1 = mismatch; learn mode: bit0 = "not all +0.0", bit1 = "not all -0.0"
+    int nseg;
+};
+
+template <bool LEARN>
+__global__ void __launch_bounds__(256)
+k_return_head(const __grid_constant__ SegDev sg, int nnz, const double* __restrict__ vals, double* __restrict__ host_vals)
+{
+    const int lane = threadIdx.x & 31;
+    const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (s >= sg.nseg) return;
+    const size_t base = (size_t)blockIdx.y * (size_t)nnz + (size_t)sg.off[s];
+    const int len = sg.len[s];
+    const double* __restrict__ src = vals + base;
+    if (LEARN) {
+        const long long negz = (long long)0x8000000000000000ULL;
+        int bits = 0;
+        for (int i = lane; i < len; i += 32) {
+            const long long v = __double_as_longlong(__ldcs(src + i));
+            bits |= (v != 0 ? 1 : 0) | (v != negz ? 2 : 0);
+        }
+        bits = __reduce_or_sync(0xffffffffu, bits);
+        if (lane == 0 && (sg.flags[s] & bits) != bits) atomicOr(sg.flags + s, bits);
+    } else if (sg.on[s]) {
+        double* __restrict__ dst = host_vals + base;
+        for (int i = lane; i < len; i += 32) dst[i] = __ldcs(src + i);
+    } else {
+        const long long f = sg.fill[s];
+        bool bad = false;
+        for (int i = lane; i < len; i += 32) bad |= __double_as_longlong(__ldcs(src + i)) != f;
+        if (__any_sync(0xffffffffu, bad) && lane == 0) sg.flags[s] = 1;
+    }
+}
+
 // self-test of FdDiv (lpb_kernels.cuh): pseudo-random operand pairs, shared-reciprocal quotient
 // vs the compiler's IEEE division, compared bit for bit
 __device__ __forceinline__ unsigned long long splitmix64(unsigned long long& s)
@@ -332,6 +382,22 @@ struct lpb_handle {
     std::vector<double> h_ctail;
     int host_fill_const = 1; // option "host_fill_const"
     int host_threads = 0;    // option "host_threads": threads of the constant-tail fill (0 = min(hardware threads, 16))
+    // sparse return of the head [NL] (k_return_head): segment table of one instance's head, the segments
+    // seen non-zero so far, and the host's fill plan (zero runs of the off-segments + the constant tail)
+    int sparse_return = 1;   // option "sparse_return"
+    int debug_skip = 0;      // option "debug_skip" (measurement only): 1 = no host fill, 2 = no return of the head
+    std::vector<int> seg_off, seg_len;
+    std::vector<unsigned char> seg_on, seg_maskable;
+    bool seg_mask_init = false;
+    std::vector<long long> seg_fill; // bit pattern of an off segment (+0.0 or -0.0)
+    struct FillRun { size_t off, len; long long bits; };
+    std::vector<FillRun> fill_runs;
+    size_t on_doubles = 0;   // doubles per instance that cross PCIe on the sparse path
+    DevBuf<int> d_seg_off, d_seg_len, d_seg_flags;
+    DevBuf<long long> d_seg_fill;
+    DevBuf<unsigned char> d_seg_on;
+    int* h_seg_flags = nullptr; // pinned
+    long long sparse_calls = 0, sparse_fixups = 0;
     lpb_handle() { std::memset(&pd, 0, sizeof pd); std::memset(&lay, 0, sizeof lay); std::memset(&ltab, 0, sizeof ltab); std::memset(&opts, 0, sizeof opts); }
     ~lpb_handle()
     {
@@ -339,6 +405,7 @@ struct lpb_handle {
             for (auto& pr : *v) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
         if (own_stream && stream) cudaStreamDestroy(stream);
         for (cudaStream_t p : pipe) if (p) cudaStreamDestroy(p);
+        if (h_seg_flags) cudaFreeHost(h_seg_flags);
     }
 };
 
@@ -492,9 +559,55 @@ static void refresh(lpb_handle* h)
                                cudaMemcpyDeviceToHost, h->stream));
         }
     }
+    // segment table of the head for the sparse return: every (row block, column block) of a phase's node
+    // part is one maskable segment of N values; event rows and link entries are always returned
+    {
+        h->seg_off.clear(); h->seg_len.clear(); h->seg_maskable.clear();
+        auto add = [&](long long off, long long len, bool maskable) {
+            if (len <= 0) return;
+            h->seg_off.push_back((int)off); h->seg_len.push_back((int)len); h->seg_maskable.push_back(maskable ? 1 : 0);
+        };
+        for (int ip = 0; ip < P; ++ip) {
+            const int N = L.ph[ip].N;
+            const int nblk = (ns + np) * (ns + nc + 2);
+            for (int b = 0; b < nblk; ++b) add(L.nl0[ip] + (long long)b * N, N, true);
+            const long long ev_end = ip + 1 < P ? L.nl0[ip + 1] : (Lp > 0 ? L.lkv0[0] : L.lin_val0);
+            add(L.ev0[ip], ev_end - L.ev0[ip], false);
+        }
+        if (Lp > 0) add(L.lkv0[0], L.lin_val0 - L.lkv0[0], false);
+        h->seg_on.assign(h->seg_off.size(), 0);
+        h->seg_fill.assign(h->seg_off.size(), 0LL);
+        h->seg_mask_init = false;
+        h->d_seg_off.upload(h->seg_off, h->stream);
+        h->d_seg_len.upload(h->seg_len, h->stream);
+        h->d_seg_on.upload(h->seg_on, h->stream);
+        h->d_seg_fill.upload(h->seg_fill, h->stream);
+        h->d_seg_flags.reserve(h->seg_off.size() + 1);
+        if (h->h_seg_flags) { cudaFreeHost(h->h_seg_flags); h->h_seg_flags = nullptr; }
+        CK(cudaMallocHost((void**)&h->h_seg_flags, (h->seg_off.size() + 1) * sizeof(int)));
+    }
     CK(cudaStreamSynchronize(h->stream));
     h->fresh = true;
     h->err_fresh = false;
+}
+
+// after the set of on-segments changed: device copy of the mask and the host's fill plan
+static void rebuild_sparse_plan(lpb_handle* h)
+{
+    const size_t nseg = h->seg_off.size();
+    h->fill_runs.clear();
+    h->on_doubles = 0;
+    for (size_t s = 0; s < nseg; ++s) {
+        if (!h->seg_maskable[s]) h->seg_on[s] = 1;
+        if (h->seg_on[s]) { h->on_doubles += (size_t)h->seg_len[s]; continue; }
+        const size_t off = (size_t)h->seg_off[s], len = (size_t)h->seg_len[s];
+        if (!h->fill_runs.empty() && h->fill_runs.back().off + h->fill_runs.back().len == off && h->fill_runs.back().bits == h->seg_fill[s])
+            h->fill_runs.back().len += len;
+        else h->fill_runs.push_back({off, len, h->seg_fill[s]});
+    }
+    h->d_seg_on.upload(h->seg_on, h->stream);
+    h->d_seg_fill.upload(h->seg_fill, h->stream);
+    CK(cudaStreamSynchronize(h->stream));
 }
 
 static void need_fresh(lpb_handle* h)
@@ -847,6 +960,37 @@ static void stream_copy(double* dst, const double* src, size_t n)
 #endif
 }
 
+static void stream_fill(double* dst, size_t n, long long bits)
+{
+#if defined(__SSE2__)
+    size_t i = 0;
+    const __m128d z = _mm_castsi128_pd(_mm_set1_epi64x(bits));
+    if (((uintptr_t)dst & 15u) && n) { _mm_stream_si64((long long*)dst, bits); i = 1; }
+    for (; i + 2 <= n; i += 2) _mm_stream_pd(dst + i, z);
+    if (i < n) _mm_stream_si64((long long*)(dst + i), bits);
+#else
+    for (size_t i = 0; i < n; ++i) std::memcpy(dst + i, &bits, sizeof bits);
+#endif
+}
+
+static int launch_return_head(lpb_handle* h, cudaStream_t st, int nb, const double* d_vals, double* host_vals_dev)
+{
+    SegDev sg;
+    sg.off = h->d_seg_off.p; sg.len = h->d_seg_len.p; sg.on = h->d_seg_on.p; sg.fill = h->d_seg_fill.p; sg.flags = h->d_seg_flags.p;
+    sg.nseg = (int)h->seg_off.size();
+    const size_t nnz = (size_t)h->pd.nnz_jac;
+    int launches = 0;
+    for (int b0 = 0; b0 < nb; b0 += 65535) {
+        const int cnt = nb - b0 < 65535 ? nb - b0 : 65535;
+        const dim3 grid((unsigned)((sg.nseg + 7) / 8), (unsigned)cnt);
+        if (host_vals_dev) k_return_head<false><<<grid, 256, 0, st>>>(sg, h->pd.nnz_jac, d_vals + (size_t)b0 * nnz, host_vals_dev + (size_t)b0 * nnz);
+        else k_return_head<true><<<grid, 256, 0, st>>>(sg, h->pd.nnz_jac, d_vals + (size_t)b0 * nnz, nullptr);
+        ++launches;
+    }
+    CK(cudaGetLastError());
+    return launches;
+}
+
 int lpb_eval_g_jac_batch(lpb_handle* h, int nbatch, const double* x, double* g, double* values)
 {
     LPB_API_BEGIN(h)
@@ -861,8 +1005,21 @@ int lpb_eval_g_jac_batch(lpb_handle* h, int nbatch, const double* x, double* g, 
     // tail into the caller's array while the DMA engine brings back the x-dependent head [NL].
     const size_t head = (size_t)h->pd.lin_val0, tail = nnz - head;
     const bool host_tail = values && h->host_fill_const && tail > 0;
+    // Sparse return of the head (k_return_head): needs the caller's array to be pinned (device-visible),
+    // and pays off only when the batch is large enough to be PCIe-bound.  The first such call on a mesh
+    // returns the head densely and learns which segments are non-zero.
+    double* values_dev = nullptr;
+    if (host_tail && h->sparse_return && head > 0 && (size_t)nbatch * head * sizeof(double) >= ((size_t)4 << 20)) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, values) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
+            values_dev = static_cast<double*>(at.devicePointer);
+        else cudaGetLastError();
+    }
+    const bool learn = values_dev && !h->seg_mask_init;
+    const bool sparse = values_dev && h->seg_mask_init && h->on_doubles * 4 <= head * 3;
+    const bool flags_wanted = learn || sparse;
     std::vector<std::thread> th;
-    if (host_tail) {
+    if (host_tail && !(h->debug_skip & 1)) {
         unsigned hw = std::thread::hardware_concurrency();
         int nt = (int)(hw ? hw : 1);
         if (nt > 16) nt = 16;
@@ -870,9 +1027,15 @@ int lpb_eval_g_jac_batch(lpb_handle* h, int nbatch, const double* x, double* g, 
         if ((size_t)nbatch * tail < (size_t)1 << 16) nt = 1;
         if (nt > nbatch) nt = nbatch;
         const double* src = h->h_ctail.data();
+        const lpb_handle::FillRun* zr = sparse ? h->fill_runs.data() : nullptr;
+        const size_t nzr = sparse ? h->fill_runs.size() : 0;
         for (int t = 0; t < nt; ++t)
             th.emplace_back([=]() {
-                for (int b = t; b < nbatch; b += nt) stream_copy(values + (size_t)b * nnz + head, src, tail);
+                for (int b = t; b < nbatch; b += nt) {
+                    double* vb = values + (size_t)b * nnz;
+                    for (size_t r = 0; r < nzr; ++r) stream_fill(vb + zr[r].off, zr[r].len, zr[r].bits);
+                    stream_copy(vb + head, src, tail);
+                }
 #if defined(__SSE2__)
                 _mm_sfence();
 #endif
@@ -887,6 +1050,8 @@ int lpb_eval_g_jac_batch(lpb_handle* h, int nbatch, const double* x, double* g, 
         CK(cudaStreamCreateWithFlags(&h->pipe[1], cudaStreamNonBlocking));
     }
     const cudaStream_t user_stream = h->stream;
+    const size_t nseg = h->seg_off.size();
+    if (flags_wanted) CK(cudaMemsetAsync(h->d_seg_flags.p, 0, nseg * sizeof(int), user_stream));
     if (nchunk > 1) CK(cudaStreamSynchronize(user_stream)); // earlier work on the handle's stream comes first
     const int saved = h->opts.skip_const;
     h->opts.skip_const = host_tail ? 1 : 0;
@@ -901,12 +1066,14 @@ int lpb_eval_g_jac_batch(lpb_handle* h, int nbatch, const double* x, double* g, 
             rc = lpb_eval_g_jac_dev(h, nb, h->d_x.p + (size_t)b0 * n, g ? h->d_g.p + (size_t)b0 * m : nullptr,
                                     values ? h->d_vals.p + (size_t)b0 * nnz : nullptr);
             if (rc != LPB_OK) { err = h->err; break; }
+            if (sparse && !(h->debug_skip & 2)) h->launches += launch_return_head(h, st, nb, h->d_vals.p + (size_t)b0 * nnz, values_dev + (size_t)b0 * nnz);
             if (g) CK(cudaMemcpyAsync(g + (size_t)b0 * m, h->d_g.p + (size_t)b0 * m, (size_t)nb * m * sizeof(double), cudaMemcpyDeviceToHost, st));
             if (values && !host_tail)
                 CK(cudaMemcpyAsync(values + (size_t)b0 * nnz, h->d_vals.p + (size_t)b0 * nnz, (size_t)nb * nnz * sizeof(double), cudaMemcpyDeviceToHost, st));
-            if (host_tail && head > 0)
+            if (host_tail && head > 0 && !sparse && !(h->debug_skip & 2))
                 CK(cudaMemcpy2DAsync(values + (size_t)b0 * nnz, nnz * sizeof(double), h->d_vals.p + (size_t)b0 * nnz, nnz * sizeof(double),
                                      head * sizeof(double), (size_t)nb, cudaMemcpyDeviceToHost, st));
+            if (learn) h->launches += launch_return_head(h, st, nb, h->d_vals.p + (size_t)b0 * nnz, nullptr);
         }
     } catch (...) {
         h->stream = user_stream;
@@ -920,6 +1087,34 @@ int lpb_eval_g_jac_batch(lpb_handle* h, int nbatch, const double* x, double* g, 
     if (nchunk > 1) { CK(cudaStreamSynchronize(h->pipe[0])); CK(cudaStreamSynchronize(h->pipe[1])); }
     else CK(cudaStreamSynchronize(h->stream));
     if (rc != LPB_OK) { h->err = err; return rc; }
+    if (flags_wanted) {
+        CK(cudaMemcpyAsync(h->h_seg_flags, h->d_seg_flags.p, nseg * sizeof(int), cudaMemcpyDeviceToHost, user_stream));
+        CK(cudaStreamSynchronize(user_stream));
+        bool changed = learn;
+        for (size_t s = 0; s < nseg; ++s) {
+            const int f = h->h_seg_flags[s];
+            if (learn) {
+                // bit0: some value is not +0.0, bit1: some value is not -0.0
+                if (!(f & 1)) { h->seg_on[s] = 0; h->seg_fill[s] = 0LL; }
+                else if (!(f & 2)) { h->seg_on[s] = 0; h->seg_fill[s] = (long long)0x8000000000000000ULL; }
+                else h->seg_on[s] = 1;
+                continue;
+            }
+            if (!f || h->seg_on[s]) continue;
+            // a segment predicted to be one signed zero throughout was not: the host wrote the fill pattern
+            // there, fetch the real values
+            CK(cudaMemcpy2DAsync(values + h->seg_off[s], nnz * sizeof(double), h->d_vals.p + h->seg_off[s], nnz * sizeof(double),
+                                 (size_t)h->seg_len[s] * sizeof(double), (size_t)nbatch, cudaMemcpyDeviceToHost, user_stream));
+            ++h->sparse_fixups;
+            h->seg_on[s] = 1;
+            changed = true;
+        }
+        if (sparse) ++h->sparse_calls;
+        if (changed) {
+            h->seg_mask_init = true;
+            rebuild_sparse_plan(h); // synchronises the stream: the fix-up copies have landed
+        }
+    }
     LPB_API_END(h)
 }
 
@@ -1141,6 +1336,14 @@ int lpb_set_option_int(lpb_handle* h, const char* name, int value)
     else if (!std::strcmp(name, "block")) h->opts.block = value;
     else if (!std::strcmp(name, "host_fill_const")) h->host_fill_const = value;
     else if (!std::strcmp(name, "host_threads")) h->host_threads = value;
+    else if (!std::strcmp(name, "sparse_return")) h->sparse_return = value;
+    else if (!std::strcmp(name, "debug_skip")) h->debug_skip = value;
+    else if (!std::strcmp(name, "sparse_forget")) { // test hook: forget every learnt segment (all predicted zero)
+        need_fresh(h);
+        std::fill(h->seg_on.begin(), h->seg_on.end(), (unsigned char)0);
+        h->seg_mask_init = value != 0;
+        rebuild_sparse_plan(h);
+    }
     else if (!std::strcmp(name, "unroll_colours")) h->opts.unroll_colours = value;
     else if (!std::strcmp(name, "time_kernels")) h->time_kernels = value != 0;
     else throw ApiError(LPB_ERR_INVALID, std::string("unknown option ") + name);
@@ -1163,6 +1366,18 @@ int lpb_selftest_fd_division(long long n, unsigned long long seed, long long* mi
 }
 
 long long lpb_kernel_launch_count(const lpb_handle* h) { return h ? h->launches : 0; }
+
+int lpb_get_stat(lpb_handle* h, const char* name, long long* value)
+{
+    LPB_API_BEGIN(h)
+    if (!name || !value) throw ApiError(LPB_ERR_INVALID, "bad argument");
+    if (!std::strcmp(name, "sparse_calls")) *value = h->sparse_calls;
+    else if (!std::strcmp(name, "sparse_fixups")) *value = h->sparse_fixups;
+    else if (!std::strcmp(name, "sparse_on_doubles")) *value = h->seg_mask_init ? (long long)h->on_doubles : -1;
+    else if (!std::strcmp(name, "head_doubles")) *value = (long long)h->pd.lin_val0;
+    else throw ApiError(LPB_ERR_INVALID, std::string("unknown counter ") + name);
+    LPB_API_END(h)
+}
 
 int lpb_kernel_time(lpb_handle* h, const char* kernel, double* total_ms, int* count)
 {

@@ -55,6 +55,7 @@ SIGNATURES = {
     "lpb_structure_dev": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
     "lpb_set_option_int": (C.c_int, [_vp, C.c_char_p, C.c_int]),
     "lpb_kernel_launch_count": (C.c_longlong, [_vp]),
+    "lpb_get_stat": (C.c_int, [_vp, C.c_char_p, C.POINTER(C.c_longlong)]),
     "lpb_kernel_time": (C.c_int, [_vp, C.c_char_p, _dp, _ip]),
     "lpb_selftest_fd_division": (C.c_int, [C.c_longlong, C.c_ulonglong, C.POINTER(C.c_longlong)]),
     "lpb_num_functors": (C.c_int, []),
@@ -156,6 +157,12 @@ class TranscribedNLP:
     @property
     def kernel_launches(self):
         return int(self.lib.lpb_kernel_launch_count(self.h))
+
+    def stat(self, name):
+        """Counter of the handle (lpb_get_stat): sparse_calls, sparse_fixups, sparse_on_doubles, head_doubles."""
+        v = C.c_longlong()
+        self._ck(self.lib.lpb_get_stat(self.h, name.encode(), C.byref(v)))
+        return int(v.value)
 
     def kernel_time(self, kernel):
         """(total device ms, launches) of the named node kernel since the last call (option time_kernels)."""

@@ -1,0 +1,146 @@
+"""Sparse return of the Jacobian head through the host-pointer batch call (lpb_eval_g_jac_batch with
+pinned buffers): whatever the GPU predicts to be all-zero, the caller's array must end up holding
+exactly the device values -- compared bit for bit with the dense (pageable-buffer) return of the
+same call, whose values are pinned to the oracle by test_gpu_parity / test_golden."""
+import numpy as np
+import pytest
+
+import cases
+
+pytestmark = pytest.mark.gpu
+
+
+def _bits(a):
+    return np.ascontiguousarray(a).view(np.int64)
+
+
+def _pinned(shape, fill=np.nan):
+    import torch
+    t = torch.full(shape, float(fill), dtype=torch.float64).pin_memory()
+    return t, t.numpy()
+
+
+def _batch_inputs(op, g, nb, seed, scale=0.05):
+    base = op.guess(g.lgr_points())
+    rng = np.random.Generator(np.random.PCG64(seed))
+    return base[None, :] + scale * rng.uniform(-1, 1, (nb, base.size))
+
+
+@pytest.fixture(scope="module")
+def nlp_mod():
+    from lpopc_b200 import nlp
+    nlp.load_library()
+    return nlp
+
+
+@pytest.mark.parametrize("name,nb", [("quadrotor/u8x8", 320), ("cartpole/u8x8", 1500), ("launch/u5x4", 400)])
+def test_sparse_return_is_exact(nlp_mod, name, nb):
+    import torch
+    op = cases.build(name)
+    g = nlp_mod.TranscribedNLP(op)
+    n, m, nnz, _ = g.get_nlp_info()
+    X = [_batch_inputs(op, g, nb, 11 + k) for k in range(3)]
+    dense = [g.eval_g_jac_batch(x) for x in X]  # pageable numpy buffers: dense return
+    assert g.stat("sparse_calls") == 0
+    hx = [torch.from_numpy(x).pin_memory() for x in X]
+    tg, hg = _pinned((nb, m))
+    tv, hv = _pinned((nb, nnz))
+    head = g.stat("head_doubles")
+    assert nb * head * 8 >= 4 << 20, "batch too small to take the sparse path"
+
+    # call 1 learns the non-zero segments (dense return + device-side flags)
+    g.eval_g_jac_batch_ptr(nb, hx[0].data_ptr(), tg.data_ptr(), tv.data_ptr())
+    assert np.array_equal(_bits(hv), _bits(dense[0][1])) and np.array_equal(_bits(hg), _bits(dense[0][0]))
+    on = g.stat("sparse_on_doubles")
+    assert 0 < on <= head
+
+    # call 2 takes the sparse path into a poisoned buffer: every entry must be rewritten
+    hv[:] = np.nan
+    hg[:] = np.nan
+    g.eval_g_jac_batch_ptr(nb, hx[1].data_ptr(), tg.data_ptr(), tv.data_ptr())
+    assert np.array_equal(_bits(hv), _bits(dense[1][1])) and np.array_equal(_bits(hg), _bits(dense[1][0]))
+    if on * 4 <= head * 3:
+        assert g.stat("sparse_calls") == 1
+
+    # forget everything that was learnt: every segment is predicted zero, the flags must bring all of them back
+    g.set_option("sparse_forget", 1)
+    hv[:] = np.nan
+    before = g.stat("sparse_fixups")
+    g.eval_g_jac_batch_ptr(nb, hx[2].data_ptr(), tg.data_ptr(), tv.data_ptr())
+    assert np.array_equal(_bits(hv), _bits(dense[2][1])) and np.array_equal(_bits(hg), _bits(dense[2][0]))
+    assert g.stat("sparse_fixups") > before
+    assert g.stat("sparse_on_doubles") == on  # same set learnt again
+
+    # and the steady state after the fix-up
+    hv[:] = np.nan
+    g.eval_g_jac_batch_ptr(nb, hx[0].data_ptr(), tg.data_ptr(), tv.data_ptr())
+    assert np.array_equal(_bits(hv), _bits(dense[0][1]))
+
+
+def test_sparse_return_grows_with_the_data(nlp_mod):
+    """Learn on inputs whose Jacobian has extra zeros (hover: angles, rates and velocities exactly 0 make
+    many trigonometric derivatives vanish), then evaluate generic inputs: newly non-zero segments are fetched."""
+    import torch
+    op = cases.build("quadrotor/u8x8")
+    g = nlp_mod.TranscribedNLP(op)
+    n, m, nnz, _ = g.get_nlp_info()
+    nb = 320
+    X1 = _batch_inputs(op, g, nb, 3)
+    X0 = np.zeros_like(X1)
+    X0[:, n - 1] = 2.0  # tf
+    d0, d1 = g.eval_g_jac_batch(X0), g.eval_g_jac_batch(X1)
+    tg, hg = _pinned((nb, m))
+    tv, hv = _pinned((nb, nnz))
+    h0, h1 = torch.from_numpy(X0).pin_memory(), torch.from_numpy(X1).pin_memory()
+    g.eval_g_jac_batch_ptr(nb, h0.data_ptr(), tg.data_ptr(), tv.data_ptr())
+    on0 = g.stat("sparse_on_doubles")
+    assert np.array_equal(_bits(hv), _bits(d0[1]))
+    hv[:] = np.nan
+    g.eval_g_jac_batch_ptr(nb, h1.data_ptr(), tg.data_ptr(), tv.data_ptr())
+    assert np.array_equal(_bits(hv), _bits(d1[1])) and np.array_equal(_bits(hg), _bits(d1[0]))
+    assert g.stat("sparse_on_doubles") >= on0
+    if g.stat("sparse_on_doubles") > on0:
+        assert g.stat("sparse_fixups") > 0
+    # back to the sparser inputs: the larger mask stays (monotone), results exact
+    hv[:] = np.nan
+    g.eval_g_jac_batch_ptr(nb, h0.data_ptr(), tg.data_ptr(), tv.data_ptr())
+    assert np.array_equal(_bits(hv), _bits(d0[1]))
+
+
+def test_sparse_return_off_and_mesh_change(nlp_mod):
+    import torch
+    op = cases.build("quadrotor/u8x8")
+    g = nlp_mod.TranscribedNLP(op)
+    nb = 320
+    n, m, nnz, _ = g.get_nlp_info()
+    X = _batch_inputs(op, g, nb, 5)
+    d = g.eval_g_jac_batch(X)
+    hx = torch.from_numpy(X).pin_memory()
+    tg, hg = _pinned((nb, m))
+    tv, hv = _pinned((nb, nnz))
+    g.set_option("sparse_return", 0)
+    for _ in range(2):
+        g.eval_g_jac_batch_ptr(nb, hx.data_ptr(), tg.data_ptr(), tv.data_ptr())
+    assert g.stat("sparse_calls") == 0 and np.array_equal(_bits(hv), _bits(d[1]))
+    g.set_option("sparse_return", 1)
+    for _ in range(2):
+        g.eval_g_jac_batch_ptr(nb, hx.data_ptr(), tg.data_ptr(), tv.data_ptr())
+    assert g.stat("sparse_calls") == 1
+    # a new mesh forgets the learnt segments (offsets change)
+    mesh, nodes = np.linspace(-1, 1, 5), [6, 6, 6, 6]
+    op.phases[0].set_mesh(mesh, nodes)
+    g.set_mesh(0, mesh, nodes)
+    g.refresh()
+    assert g.stat("sparse_on_doubles") == -1
+    n2, m2, nnz2, _ = g.get_nlp_info()
+    X2 = _batch_inputs(op, g, nb, 6)
+    assert X2.shape == (nb, n2)
+    d2 = g.eval_g_jac_batch(X2)
+    tv2, hv2 = _pinned((nb, nnz2))
+    tg2, hg2 = _pinned((nb, m2))
+    hx2 = torch.from_numpy(X2).pin_memory()
+    for _ in range(2):
+        hv2[:] = np.nan
+        g.eval_g_jac_batch_ptr(nb, hx2.data_ptr(), tg2.data_ptr(), tv2.data_ptr())
+        assert np.array_equal(_bits(hv2), _bits(d2[1])) and np.array_equal(_bits(hg2), _bits(d2[0]))
+    assert g.stat("sparse_calls") == 2
