@@ -30,6 +30,18 @@
  * forward-difference quotients (cancellation-amplified by 1/h ~ 1e6) within the
  * 1e-12 parity bound.  No fast-math: NaN must propagate (dependency probe,
  * LpDerivDependciesChecker.cpp:61-94).
+ *
+ * Optional member `dae_sweep` (flagged by `static constexpr bool HAS_SWEEP = true`), the finite-difference
+ * counterpart of the reference's optional user derivatives (LpFunctionWrapper.h Deriv*): dynamics with DENSE
+ * dependencies can evaluate the base point and all ns+nc+1 single-variable perturbations of the reference's
+ * column-by-column scheme (LpFiniteDifferenceDerive.cpp:245-259) in one pass that shares the unchanged work,
+ *     template <class K> static void dae_sweep(c, phase, t, x, u, f, path, K& k);
+ * filling f/path like dae() and, per colour cc in [x.., u.., t] order, calling
+ *     vp = k.begin(cc, v)                  v = the variable's value; returns the perturbed value v + h
+ *     k.state_row(cc, s, fp, f[s])         fp = f_s at the perturbed point
+ *     k.path_row(cc, i, cp, path[i])
+ * once per row.  The values passed must be exactly what dae() returns at the perturbed point (same operations,
+ * same order); the kernels do the quotients and the scatter.  Without the hook the kernels call dae() per colour.
  */
 #ifndef LPB_FUNCTOR_H
 #define LPB_FUNCTOR_H
