@@ -266,7 +266,6 @@ class BlockTridiagKKT:
         self.mr = mr
         self.dpos = rmin * mr + rpos                          # equality row -> slot in the padded [K*mr] layout
         self.j_sel = sel
-        self.j_flat = (self.dpos[rr] * (2 * nb)) + (cb - rmin[rr]) * nb + pos[c[sel]]
         # Hessian entries (lower triangle of the global matrix): same block -> D (both triangles), adjacent -> E
         hr, hc = colmap[ev.hI], colmap[ev.hJ]
         hs = torch.nonzero((hr >= 0) & (hc >= 0)).squeeze(1)
@@ -285,8 +284,26 @@ class BlockTridiagKKT:
         lo = torch.where(lo_is_c, bc[adj], br[adj])
         p_hi = torch.where(lo_is_c, pr[adj], pc[adj])
         p_lo = torch.where(lo_is_c, pc[adj], pr[adj])
+        # Boundary variables: the only slots of block i+1 that block i couples to (rows of E).  The defect rows of
+        # interval i read just the first node of interval i+1 (column overlap 1 of the composite D matrix,
+        # RPMGenerator.cpp:150-160), so E = [nbd x nb] with nbd ~ ns << nb: the off-diagonal solves, the rank
+        # update of the next diagonal block and the J^T J product all shrink from nb to nbd rows.
+        nxt = (cb - rmin[rr]) == 1
+        bmask = torch.zeros(nb, dtype=torch.bool, device=dev)
+        bmask[pos[c[sel]][nxt]] = True
+        bmask[p_hi] = True
+        if not bool(bmask.any()):
+            bmask[0] = True                                   # decoupled blocks: one dummy boundary slot (E stays zero)
+        self.bnd = torch.nonzero(bmask).squeeze(1)            # slots (same set for every block: union over blocks)
+        nbd = int(self.bnd.numel())
+        self.nbd = nbd
+        bidx = torch.full((nb,), -1, dtype=torch.int64, device=dev)
+        bidx[self.bnd] = torch.arange(nbd, device=dev)
+        self.ncol = nb + nbd
+        jcol = torch.where(nxt, nb + bidx[pos[c[sel]]], pos[c[sel]])
+        self.j_flat = self.dpos[rr] * self.ncol + jcol        # Jb[row slot][own block | boundary of the next block]
         self.he_sel = hs[adj]
-        self.he_flat = (lo * nb + p_hi) * nb + p_lo           # E[lo][p_hi][p_lo]: rows of block lo+1, cols of block lo
+        self.he_flat = (lo * nbd + bidx[p_hi]) * nb + p_lo  # E[lo][boundary slot of block lo+1][col of block lo]
         real = torch.zeros(K * nb, dtype=torch.bool, device=dev)
         real[self.fpos] = True
         self.pad_diag = (~real).to(torch.float64).view(K, nb)  # 1 on padded slots (keeps the blocks non-singular)
@@ -310,18 +327,22 @@ class BlockTridiagKKT:
 
     def set_jac(self, jv):
         B = jv.shape[0]
-        Jb = torch.zeros((B, self.K * self.mr * 2 * self.nb), dtype=torch.float64, device=jv.device)
+        Jb = torch.zeros((B, self.K * self.mr * self.ncol), dtype=torch.float64, device=jv.device)
         Jb.index_add_(1, self.j_flat, jv[:, self.j_sel])
-        self.Jb = Jb.view(B, self.K, self.mr, 2 * self.nb)
+        self.Jb = Jb.view(B, self.K, self.mr, self.ncol)
+
+    def _next_bnd(self, xb):   # [B, K, nb] -> boundary slots of the following block [B, K, nbd] (zeros after the last)
+        nxt = xb[:, 1:, self.bnd]
+        return torch.cat([nxt, torch.zeros_like(nxt[:, :1])], 1) if self.K > 1 else torch.zeros_like(xb[:, :, self.bnd])
 
     def _Jmul(self, xb):       # [B, K, nb] -> [B, K, mr]
-        nxt = torch.cat([xb[:, 1:], torch.zeros_like(xb[:, :1])], 1)
-        return torch.einsum("bkmn,bkn->bkm", self.Jb, torch.cat([xb, nxt], 2))
+        return torch.einsum("bkmn,bkn->bkm", self.Jb, torch.cat([xb, self._next_bnd(xb)], 2))
 
     def _Jtmul(self, vb):      # [B, K, mr] -> [B, K, nb]
         y = torch.einsum("bkmn,bkm->bkn", self.Jb, vb)
         out = y[:, :, :self.nb].clone()
-        out[:, 1:] += y[:, :-1, self.nb:]
+        if self.K > 1:
+            out[:, 1:, self.bnd] += y[:, :-1, self.nb:]
         return out
 
     def Jt(self, v):
@@ -329,23 +350,26 @@ class BlockTridiagKKT:
 
     def _Hmul(self, D, E, xb):
         out = torch.einsum("bkij,bkj->bki", D, xb)
-        if self.K > 1:
-            out[:, 1:] += torch.einsum("bkij,bkj->bki", E, xb[:, :-1])
-            out[:, :-1] += torch.einsum("bkij,bki->bkj", E, xb[:, 1:])
+        if self.K > 1 and self.he_sel.numel():
+            out[:, 1:, self.bnd] += torch.einsum("bkij,bkj->bki", E, xb[:, :-1])
+            out[:, :-1] += torch.einsum("bkij,bki->bkj", E, xb[:, 1:, self.bnd])
         return out
 
     def _factor(self, Dp, Ep):
-        """Block-tridiagonal Cholesky: returns (list L_i, list C_i, info)."""
+        """Block-tridiagonal Cholesky with boundary-row off-diagonal blocks: L_i L_i^T = A_i - (C_i C_i^T on the
+        boundary slots), C_i = E_i L_{i-1}^-T [nbd x nb].  Returns (list L_i, list C_i, info)."""
         Ls, Cs = [], []
         info = torch.zeros(Dp.shape[0], dtype=torch.int32, device=Dp.device)
         eye = torch.eye(self.nb, dtype=torch.float64, device=Dp.device)
+        bi = self.bnd
         prev = None
         for i in range(self.K):
             A = Dp[:, i]
             if i > 0:
                 C = torch.linalg.solve_triangular(prev, Ep[:, i - 1].transpose(1, 2), upper=False).transpose(1, 2)  # E L^-T
                 Cs.append(C)
-                A = A - torch.bmm(C, C.transpose(1, 2))
+                A = A.clone()
+                A[:, bi.unsqueeze(1), bi.unsqueeze(0)] -= torch.bmm(C, C.transpose(1, 2))
             L, inf_i = torch.linalg.cholesky_ex(A)
             bad = inf_i != 0
             info = torch.where((info == 0) & bad, inf_i, info)
@@ -355,43 +379,48 @@ class BlockTridiagKKT:
         return Ls, Cs, info
 
     def _solve(self, Ls, Cs, rb):
+        bi = self.bnd
         ys = []
         for i in range(self.K):
             t = rb[:, i]
             if i > 0:
-                t = t - torch.bmm(Cs[i - 1], ys[-1].unsqueeze(2)).squeeze(2)
+                t = t.clone()
+                t[:, bi] -= torch.bmm(Cs[i - 1], ys[-1].unsqueeze(2)).squeeze(2)
             ys.append(torch.linalg.solve_triangular(Ls[i], t.unsqueeze(2), upper=False).squeeze(2))
         xs = [None] * self.K
         for i in range(self.K - 1, -1, -1):
             t = ys[i]
             if i + 1 < self.K:
-                t = t - torch.bmm(Cs[i].transpose(1, 2), xs[i + 1].unsqueeze(2)).squeeze(2)
+                t = t - torch.bmm(Cs[i].transpose(1, 2), xs[i + 1][:, bi].unsqueeze(2)).squeeze(2)
             xs[i] = torch.linalg.solve_triangular(Ls[i].transpose(1, 2), t.unsqueeze(2), upper=True).squeeze(2)
         return torch.stack(xs, 1)
 
     def step(self, hv, Sigma, rhs1, c, dw_last, done):
-        B, K, nb, g = hv.shape[0], self.K, self.nb, self.gamma
+        B, K, nb, nbd, g = hv.shape[0], self.K, self.nb, self.nbd, self.gamma
         dev = hv.device
+        bi = self.bnd
         D = torch.zeros((B, K * nb * nb), dtype=torch.float64, device=dev)
         D.index_add_(1, self.hd_flat, hv[:, self.hd_sel])
         D = D.view(B, K, nb, nb)
-        E = torch.zeros((B, max(K - 1, 1) * nb * nb), dtype=torch.float64, device=dev)
+        E = torch.zeros((B, max(K - 1, 1) * nbd * nb), dtype=torch.float64, device=dev)
         if self.he_sel.numel():
             E.index_add_(1, self.he_flat, hv[:, self.he_sel])
-        E = E.view(B, max(K - 1, 1), nb, nb)
+        E = E.view(B, max(K - 1, 1), nbd, nb)
         di = torch.arange(nb, device=dev)
         base = D[:, :, di, di] + self.to_blocks(Sigma) + self.pad_diag
-        G = torch.einsum("bkmi,bkmj->bkij", self.Jb, self.Jb)  # J_i^T J_i over the columns of blocks i and i+1
+        G = torch.einsum("bkmi,bkmj->bkij", self.Jb, self.Jb)  # J_i^T J_i over [own block | boundary of block i+1]
         Dp = D + g * G[:, :, :nb, :nb]
-        if K > 1:
-            Dp[:, 1:] += g * G[:, :-1, nb:, nb:]
+        if K > 1 and nbd > 0:
+            Dp[:, 1:, bi.unsqueeze(1), bi.unsqueeze(0)] += g * G[:, :-1, nb:, nb:]
             Ep = E + g * G[:, :-1, nb:, :nb]
         else:
             Ep = E
         dw = torch.where(dw_last > 0, dw_last / 3.0, torch.zeros_like(dw_last))
         dw = torch.where(dw < 1e-9, torch.zeros_like(dw), dw)
-        Gd = torch.diagonal(G, dim1=2, dim2=3)  # [B, K, 2 nb]
-        gdiag = g * (Gd[:, :, :nb] + torch.cat([torch.zeros_like(Gd[:, :1, nb:]), Gd[:, :-1, nb:]], 1))
+        Gd = torch.diagonal(G, dim1=2, dim2=3)  # [B, K, nb + nbd]
+        gdiag = g * Gd[:, :, :nb].clone()
+        if K > 1 and nbd > 0:
+            gdiag[:, 1:, bi] += g * Gd[:, :-1, nb:]
         for _try in range(40):
             Dp[:, :, di, di] = base + gdiag + dw.view(-1, 1, 1)
             Ls, Cs, info = self._factor(Dp, Ep)
@@ -479,7 +508,7 @@ class BatchedIPM:
         if self.var_blocks is not None:
             try:
                 self.kkt = BlockTridiagKKT(self, self._free_blocks())
-                self.kkt_kind = "block-tridiagonal (K=%d, nb=%d)" % (self.kkt.K, self.kkt.nb)
+                self.kkt_kind = "block-tridiagonal (K=%d, nb=%d, boundary=%d)" % (self.kkt.K, self.kkt.nb, self.kkt.nbd)
             except ValueError:
                 pass  # coupling does not fit (free phase times, x0-xf Mayer terms, ...): dense step
 
