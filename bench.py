@@ -261,6 +261,12 @@ def main():
         run_reference(args, rank, world)
         return
 
+    # stdout carries exactly one JSON line: anything libraries print on fd 1 meanwhile (NCCL's version banner,
+    # warnings) is routed to stderr until rank 0 prints the result
+    sys.stdout.flush()
+    stdout_fd = os.dup(1)
+    os.dup2(2, 1)
+
     cpu = None
     if rank == 0 and not args.no_cpu:
         # CPU leg first: it forks worker processes, which must happen before CUDA is initialised
@@ -481,7 +487,10 @@ def main():
         line.update(extras)
         if solves:
             line["solves"] = solves
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(stdout_fd, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 
