@@ -137,6 +137,17 @@ int lpb_mesh_error(lpb_handle* h, const double* x, int* rows_out, double* rel_er
 int lpb_refine_mesh_ph(lpb_handle* h, const double* x, double tol, int Nmax, int Nmin, int* no_more_refine,
                        int* K_out, double* mesh_out, int* nodes_out);
 
+/* ---- NLP solution -> optimal-control solution (the step right after the solve) ----
+ * Replaces: Nlp2OpConverter::Nlp2OpControl (Nlp2OPConverter.cpp:13-196).  From the NLP solution x and the
+ * constraint multipliers lambda (IPOPT's sign, as in finalize_solution, LpopcIpopt.cpp:220) the GPU builds,
+ * per phase with N nodes (M = N + 1 rows, column-major), phases concatenated in `out`:
+ *   time[M] | state[M x ns] | control[M x nc] | costate[M x ns] | pathmult[M x np] | Hamiltonian[M] | mayer, lagrange
+ * (control / pathmult end rows by the reference's natural cubic spline, terminal costate through the last
+ * column of D).  lpb_nlp2op_length returns the number of doubles `out` must hold and, if phase_offsets is
+ * given, the P + 1 phase offsets into it.  total_cost (optional) = Data_->optcontrol_cost. */
+long long lpb_nlp2op_length(lpb_handle* h, long long* phase_offsets);
+int lpb_nlp2op(lpb_handle* h, const double* x, const double* lambda, double* out, double* total_cost);
+
 /* ---- batched independent instances (MPC-style; BASELINE config 4) ----------
  * nbatch instances share problem, mesh, tables and pattern; instance b uses
  * x[b*n .. b*n+n).  Host-pointer versions copy H2D/D2H around the kernels. */

@@ -378,7 +378,7 @@ struct lpb_handle {
     // rows and the Doffdiag entries), cached on the host at refresh
     bool err_fresh = false; // mesh-error tables match the current mesh
     MeshErrDev med;
-    DevBuf<double> d_tem, d_abserr;
+    DevBuf<double> d_tem, d_abserr, d_conv;
     std::vector<double> h_ctail;
     int host_fill_const = 1; // option "host_fill_const"
     int host_threads = 0;    // option "host_threads": threads of the constant-tail fill (0 = min(hardware threads, 16))
@@ -1305,6 +1305,42 @@ int lpb_refine_mesh_ph(lpb_handle* h, const double* x, double tol, int Nmax, int
         kn += nn.size();
     }
     *no_more_refine = done ? 1 : 0;
+    LPB_API_END(h)
+}
+
+long long lpb_nlp2op_length(lpb_handle* h, long long* phase_offsets)
+{
+    if (!h) return LPB_ERR_INVALID;
+    try {
+        need_fresh(h);
+        long long off[kMaxPhases + 1];
+        h->vt->nlp2op(h->pd, h->consts.data(), h->stream, nullptr, nullptr, nullptr, nullptr, off);
+        if (phase_offsets) std::memcpy(phase_offsets, off, (size_t)(h->pd.P + 1) * sizeof(long long));
+        return off[h->pd.P];
+    } catch (const ApiError& e) { h->err = e.what(); return e.code; }
+    catch (const std::exception& e) { h->err = e.what(); return LPB_ERR_INVALID; }
+}
+
+int lpb_nlp2op(lpb_handle* h, const double* x, const double* lambda, double* out, double* total_cost)
+{
+    LPB_API_BEGIN(h)
+    need_fresh(h);
+    if (!x || !lambda || !out) throw ApiError(LPB_ERR_INVALID, "bad argument");
+    long long off[kMaxPhases + 1];
+    h->vt->nlp2op(h->pd, h->consts.data(), h->stream, nullptr, nullptr, nullptr, nullptr, off);
+    const size_t len = (size_t)off[h->pd.P];
+    h2d(h, h->d_x, x, (size_t)h->pd.n);
+    h2d(h, h->d_lambda, lambda, (size_t)h->pd.m);
+    h->d_conv.reserve(len);
+    ensure_scratch(h, 1);
+    note_launches(h, h->vt->nlp2op(h->pd, h->consts.data(), h->stream, h->d_x.p, h->d_lambda.p, h->d_conv.p, h->d_scratch.p, nullptr));
+    d2h(h, out, h->d_conv.p, len);
+    CK(cudaStreamSynchronize(h->stream));
+    if (total_cost) { // Data_->optcontrol_cost: phases in order, mayer + lagrange (Nlp2OPConverter.cpp:138)
+        double c = 0.0;
+        for (int p = 0; p < h->pd.P; ++p) c += out[off[p + 1] - 2] + out[off[p + 1] - 1];
+        *total_cost = c;
+    }
     LPB_API_END(h)
 }
 

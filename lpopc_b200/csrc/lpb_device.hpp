@@ -119,6 +119,9 @@ struct FunctorVTable {
     size_t (*scratch_doubles)(const ProblemDev& pd, int nbatch);
     int (*mesh_error)(const ProblemDev& pd, const void* consts, cudaStream_t st, const MeshErrDev& me, int total_intervals, int max_n,
                       const double* x, double* tem, double* abs_err);
+    // NLP solution -> optimal-control solution (lpb_convert.cuh); out == nullptr: layout query only
+    int (*nlp2op)(const ProblemDev& pd, const void* consts, cudaStream_t st, const double* x, const double* lambda,
+                  double* out, double* scratch, long long* phase_offsets);
 };
 
 const FunctorVTable* const* functor_registry(int* count);

@@ -17,6 +17,7 @@
 #pragma once
 #include "lpb_kernels.cuh"
 #include "lpb_mesherr.cuh"
+#include "lpb_convert.cuh"
 
 namespace lpb {
 
@@ -428,7 +429,7 @@ const FunctorVTable* make_vtable()
         P::name(), P::NS, P::NC, P::NPATH, P::NE_MAX, P::NL_MAX,
         (int)(sizeof(typename P::Consts) / sizeof(double)), P::HAS_ANALYTIC ? 1 : 0,
         &launch_cons_jac<P>, &launch_objective<P>, &launch_gradient<P>, &launch_hessian<P>, &launch_probe<P>,
-        &scratch_doubles<P>, &launch_mesh_error<P>};
+        &scratch_doubles<P>, &launch_mesh_error<P>, &launch_nlp2op<P>};
     return &vt;
 }
 

@@ -55,6 +55,8 @@ SIGNATURES = {
     "lpb_structure_dev": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
     "lpb_set_option_int": (C.c_int, [_vp, C.c_char_p, C.c_int]),
     "lpb_kernel_launch_count": (C.c_longlong, [_vp]),
+    "lpb_nlp2op_length": (C.c_longlong, [_vp, C.POINTER(C.c_longlong)]),
+    "lpb_nlp2op": (C.c_int, [_vp, _dp, _dp, _dp, _dp]),
     "lpb_get_stat": (C.c_int, [_vp, C.c_char_p, C.POINTER(C.c_longlong)]),
     "lpb_kernel_time": (C.c_int, [_vp, C.c_char_p, _dp, _ip]),
     "lpb_selftest_fd_division": (C.c_int, [C.c_longlong, C.c_ulonglong, C.POINTER(C.c_longlong)]),
@@ -107,6 +109,24 @@ class LpopcError(RuntimeError):
         self.code = code
 
 
+def unpack_nlp2op(out, shapes):
+    """Flat lpb_nlp2op output -> per-phase dict; shapes = [(M, ns, nc, np)] with M = N + 1 rows (column-major)."""
+    res, k = [], 0
+    for M, ns, nc, npth in shapes:
+        d = {}
+        for key, cols in (("time", None), ("state", ns), ("control", nc), ("costate", ns), ("pathmult", npth), ("hamiltonian", None)):
+            if cols is None:
+                d[key] = out[k:k + M].copy()
+                k += M
+            else:
+                d[key] = out[k:k + M * cols].reshape(cols, M).T.copy()
+                k += M * cols
+        d["mayer"], d["lagrange"] = float(out[k]), float(out[k + 1])
+        k += 2
+        res.append(d)
+    return res
+
+
 class TranscribedNLP:
     """The NLP that the interior-point solver sees, evaluated on the GPU."""
 
@@ -157,6 +177,20 @@ class TranscribedNLP:
     @property
     def kernel_launches(self):
         return int(self.lib.lpb_kernel_launch_count(self.h))
+
+    def nlp2op(self, x, lam):
+        """NLP solution + multipliers -> optimal-control solution on the GPU (Nlp2OpConverter::Nlp2OpControl,
+        Nlp2OPConverter.cpp:13-196): ([dict(time, state, control, costate, pathmult, hamiltonian, mayer, lagrange)
+        per phase], total cost)."""
+        x, lam = _f64(x), _f64(lam)
+        n = int(self.lib.lpb_nlp2op_length(self.h, None))
+        if n < 0:
+            self._ck(n)
+        out = np.empty(n)
+        tot = C.c_double()
+        self._ck(self.lib.lpb_nlp2op(self.h, _d(x), _d(lam), _d(out), C.byref(tot)))
+        shapes = [(int(sum(p.nodesperinterval)) + 1, len(p.statemin), len(p.controlmin), len(p.pathmin)) for p in self.op.phases]
+        return unpack_nlp2op(out, shapes), tot.value
 
     def stat(self, name):
         """Counter of the handle (lpb_get_stat): sparse_calls, sparse_fixups, sparse_on_doubles, head_doubles."""

@@ -54,6 +54,13 @@ def main():
             d["refine_%s_done" % tag] = np.array(int(done))
             for ip, (mp, nd) in enumerate(meshes):
                 d["refine_%s_mesh%d" % (tag, ip)], d["refine_%s_nodes%d" % (tag, ip)] = mp, nd
+        # NLP solution -> optimal-control solution at (x, lam) (Nlp2OpConverter::Nlp2OpControl)
+        res, tot = r.nlp2op(x, lam)
+        d["n2o_cost"] = np.array(tot)
+        for ip, q in enumerate(res):
+            for key in ("time", "state", "control", "costate", "pathmult", "hamiltonian"):
+                d["n2o_%s%d" % (key, ip)] = q[key]
+            d["n2o_costs%d" % ip] = np.array([q["mayer"], q["lagrange"]])
         if name == "launch":  # dependency probe + the sparse Hessian pattern it implies
             d["dep"] = r.probe_dependencies(guess)
             d["dep_info"] = np.array(r.nlp_info())

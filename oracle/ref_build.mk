@@ -18,7 +18,7 @@ CXXFLAGS := -std=c++14 -O2 -w -fPIC -ffp-contract=off -include functional \
 REF_SRCS := SparseMatrix/LpSparseMatrix.cpp SparseMatrix/LpSparseArray.cpp \
             Core/RPMGenerator.cpp Core/LpSizeChecker.cpp Core/LpBoundsChecker.cpp Core/LpOptimalProblem.cpp \
             Core/LpGuessChecker.cpp Core/LpDerivDependciesChecker.cpp Core/LpFiniteDifferenceDerive.cpp \
-            Core/LpNLPWrapper.cpp Core/LpHessian.cpp Core/LpSacleOCP.cpp Core/LpSolutionError.cpp Core/LpPhMeshRefineAlg.cpp \
+            Core/LpNLPWrapper.cpp Core/LpHessian.cpp Core/LpSacleOCP.cpp Core/LpSolutionError.cpp Core/LpPhMeshRefineAlg.cpp Core/Nlp2OPConverter.cpp \
             Common/LpOption.cpp Common/LpOptionList.cpp Common/LpReporter.cpp Common/LpDebug.cpp Common/LpUtils.cpp
 OBJS := $(addprefix $(OUT)/,$(notdir $(REF_SRCS:.cpp=.o))) $(OUT)/ref_driver.o
 HDRS := oracle/ref_shim/armadillo $(wildcard include/*.h) $(wildcard include/problems/*.h)

@@ -28,6 +28,7 @@
 #include "LpPhMeshRefineAlg.hpp"
 #include "LpSizeChecker.h"
 #include "LpSolutionError.h"
+#include "Nlp2OPConverter.h"
 #include "spdlog/sinks/null_sink.h"
 #include "RPMGenerator.hpp"
 
@@ -598,6 +599,41 @@ int lpo_refine_ph(void* h, const double* x, double tol, int Nmax, int Nmin, int*
             for (size_t i = 0; i < meshes[ip]->nodesPerInterval.n_elem; ++i) nodes_out[kn++] = (int)meshes[ip]->nodesPerInterval(i);
         }
         r->fresh = false; // RefineMesh rewrote the mesh inside r->op; the next call rebuilds from r->ph
+    })
+}
+
+// Nlp2OpConverter::Nlp2OpControl (Core/Nlp2OPConverter.cpp:13-196) on the NLP solution x and multipliers
+// lambda.  Output per phase (M = N + 1 rows, column-major), phases concatenated:
+//   time[M] | state[M x ns] | control[M x nc] | costate[M x ns] | pathmult[M x np] | Hamiltonian[M] | mayer, lagrange
+int lpo_nlp2op(void* h, const double* x, const double* lambda, double* out, double* total_cost)
+{
+    Ref* r = (Ref*)h;
+    REF_GUARD(r, {
+        if (!r->fresh) refresh(*r);
+        const size_t m = r->cd->conbounds_min.size() + r->cd->linmin.n_elem;
+        r->cd->nlpreturn_x = xvec(r, x);
+        vec lam(m);
+        for (size_t i = 0; i < m; ++i) lam(i) = lambda[i];
+        r->cd->nlpreturn_lambda = lam;
+        r->cd->autoscale = false;
+        Nlp2OpConverter conv;
+        conv.Nlp2OpControl(r->fun, r->cd, r->op);
+        size_t k = 0;
+        for (size_t ip = 0; ip < r->ph.size(); ++ip) {
+            const SolutionData& sd = *r->cd->result[ip];
+            const int ns = r->ph[ip].d.nstates, nc = r->ph[ip].d.ncontrols, np = r->ph[ip].d.npaths;
+            const size_t M = sd.time.n_elem;
+            for (size_t i = 0; i < M; ++i) out[k++] = sd.time(i);
+            for (size_t i = 0; i < M * ns; ++i) out[k++] = sd.state[i];
+            for (size_t i = 0; i < M * nc; ++i) out[k++] = sd.control[i];
+            for (size_t i = 0; i < M * ns; ++i) out[k++] = sd.costate[i];
+            for (size_t i = 0; i < M * np; ++i) out[k++] = sd.pathmult[i];
+            for (size_t i = 0; i < M; ++i) out[k++] = sd.Hamiltonian[i];
+            out[k++] = sd.mayerCost;
+            out[k++] = sd.lagrangeCost;
+        }
+        if (total_cost) *total_cost = r->cd->optcontrol_cost;
+        r->fresh = false; // Nlp2OpControl rewrote the guesses inside r->op; the next call rebuilds from r->ph
     })
 }
 

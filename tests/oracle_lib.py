@@ -242,6 +242,17 @@ class RefOracle(Oracle):
             k += rows[ip] * ns[ip]
         return out
 
+    def nlp2op(self, x, lam):
+        """Nlp2OpConverter::Nlp2OpControl of the reference: ([dict(time, state, control, costate, pathmult,
+        hamiltonian, mayer, lagrange) per phase], total cost)."""
+        from lpopc_b200.nlp import unpack_nlp2op
+        x, lam = np.ascontiguousarray(x, dtype=np.float64), np.ascontiguousarray(lam, dtype=np.float64)
+        shapes = [(int(sum(p.nodesperinterval)) + 1, len(p.statemin), len(p.controlmin), len(p.pathmin)) for p in self.op.phases]
+        out = np.empty(sum(M * (2 + 2 * ns + nc + npth) + 2 for M, ns, nc, npth in shapes))
+        tot = C.c_double()
+        self._check(self.L.lpo_nlp2op(self.h, _d(x), _d(lam), _d(out), C.byref(tot)))
+        return unpack_nlp2op(out, shapes), tot.value
+
     def refine_ph(self, x, tol=1e-6, nmax=16, nmin=4):
         """PhMeshRefineAlg::RefineMesh of the reference: (no_more_refine, [(meshpoints, nodes) per phase])."""
         x = np.ascontiguousarray(x, dtype=np.float64)
