@@ -1381,6 +1381,7 @@ int lpb_set_option_int(lpb_handle* h, const char* name, int value)
         rebuild_sparse_plan(h);
     }
     else if (!std::strcmp(name, "unroll_colours")) h->opts.unroll_colours = value;
+    else if (!std::strcmp(name, "rotate_nodes")) h->opts.no_rotate = value ? 0 : 1;
     else if (!std::strcmp(name, "time_kernels")) h->time_kernels = value != 0;
     else throw ApiError(LPB_ERR_INVALID, std::string("unknown option ") + name);
     LPB_API_END(h)

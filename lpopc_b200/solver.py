@@ -467,10 +467,11 @@ def interval_blocks(op, n_total):
 class BatchedIPM:
     """Lockstep primal-dual interior-point method over a batch of instances of one NLP."""
 
-    def __init__(self, ev, tol=1e-6, max_iter=100, mu0=0.1, rho=1e3, verbose=False, var_blocks=None):
+    def __init__(self, ev, tol=1e-6, max_iter=100, mu0=0.1, rho=1e3, verbose=False, var_blocks=None, kkt_gamma=1e6, kkt_refine=3):
         """var_blocks: optional block id (mesh interval) per NLP variable (`interval_blocks(op, n)`): selects the
         block-tridiagonal KKT step when the problem's coupling allows it, the dense condensed step otherwise."""
         self.var_blocks = var_blocks
+        self.kkt_gamma, self.kkt_refine = kkt_gamma, kkt_refine
         self.kkt_kind = "dense"
         _, _, gl, gu = ev.bounds()
         self.user_ev = ev
@@ -507,7 +508,7 @@ class BatchedIPM:
         self.kkt_kind = "dense"
         if self.var_blocks is not None:
             try:
-                self.kkt = BlockTridiagKKT(self, self._free_blocks())
+                self.kkt = BlockTridiagKKT(self, self._free_blocks(), gamma=self.kkt_gamma, refine=self.kkt_refine)
                 self.kkt_kind = "block-tridiagonal (K=%d, nb=%d, boundary=%d)" % (self.kkt.K, self.kkt.nb, self.kkt.nbd)
             except ValueError:
                 pass  # coupling does not fit (free phase times, x0-xf Mayer terms, ...): dense step
