@@ -82,6 +82,48 @@ __global__ void __launch_bounds__(128) k_chunked(double* out, int nb, int N, siz
             for (int cc = c0; cc < c0 + CH && cc < NB; ++cc) __stcs(vb + (unsigned)(i * NB + cc) * (unsigned)N, v + cc);
 }
 
+// H: staged write-out.  CTA = 128 threads = 2 instances; per pass of CH colours the CTA holds 2 x NROW runs of
+// CH*N contiguous doubles (row i, colours c0..c0+CH-1) in shared memory and writes each run contiguously:
+// BULK = false: warps store 256-byte pieces back to back; BULK = true: one cp.async.bulk per run.
+template <int NROW, int NB, int CH, bool BULK>
+__global__ void __launch_bounds__(128) k_staged(double* out, int nb, int N, size_t pitch, double v)
+{
+    extern __shared__ __align__(128) double sm[];
+    const int b0 = blockIdx.x * 2;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int c0 = 0; c0 < NB; c0 += CH) {
+        const int ch = c0 + CH <= NB ? CH : NB - c0;
+        // "compute": every thread deposits its CH x NROW values (conflict-free: consecutive nodes)
+        const int inst = threadIdx.x / N, k = threadIdx.x % N;
+        for (int i = 0; i < NROW; ++i)
+            for (int c = 0; c < ch; ++c) sm[((inst * NROW + i) * CH + c) * N + k] = v + c;
+        if (BULK) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        const int run_len = ch * N;
+        if (BULK) {
+            if (threadIdx.x < 2 * NROW) {
+                const int r = threadIdx.x, ins = r / NROW, i = r % NROW;
+                if (b0 + ins < nb) {
+                    double* dst = out + (size_t)(b0 + ins) * pitch + (size_t)(i * NB + c0) * N;
+                    const unsigned src = (unsigned)__cvta_generic_to_shared(sm + (size_t)r * CH * N);
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(run_len * 8) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                }
+            }
+        } else {
+            for (int r = warp; r < 2 * NROW; r += 4) {
+                const int ins = r / NROW, i = r % NROW;
+                if (b0 + ins >= nb) continue;
+                double* dst = out + (size_t)(b0 + ins) * pitch + (size_t)(i * NB + c0) * N;
+                const double* src = sm + (size_t)r * CH * N;
+                for (int j = lane; j < run_len; j += 32) __stcs(dst + j, src[j]);
+            }
+        }
+        __syncthreads();
+    }
+}
+
 template <class F>
 float time_ms(F f, int reps)
 {
@@ -121,6 +163,26 @@ int main()
     printf("G chunk 4, rot      %.4f ms  %.0f GB/s\n", g4, bytes / g4 / 1e6);
     printf("G chunk 8, rot      %.4f ms  %.0f GB/s\n", g8, bytes / g8 / 1e6);
     printf("G chunk 4, no rot   %.4f ms  %.0f GB/s\n", g4n, bytes / g4n / 1e6);
+    {
+        const int CH = 5;
+        const size_t shm = (size_t)2 * 12 * CH * N * 8;
+        cudaFuncSetAttribute(k_staged<12, 19, CH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
+        cudaFuncSetAttribute(k_staged<12, 19, CH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
+        float h1 = time_ms([&] { k_staged<12, 19, CH, false><<<nb / 2, 128, shm>>>(out, nb, N, nnz, 1.0); }, 20);
+        float h2 = time_ms([&] { k_staged<12, 19, CH, true><<<nb / 2, 128, shm>>>(out, nb, N, nnz, 1.0); }, 20);
+        printf("H staged 5 colours, warp stores  %.4f ms  %.0f GB/s  (err %s)\n", h1, bytes / h1 / 1e6, cudaGetErrorString(cudaGetLastError()));
+        printf("H staged 5 colours, bulk copies  %.4f ms  %.0f GB/s  (err %s)\n", h2, bytes / h2 / 1e6, cudaGetErrorString(cudaGetLastError()));
+    }
+    {
+        const int CH = 10;
+        const size_t shm = (size_t)2 * 12 * CH * N * 8;
+        cudaFuncSetAttribute(k_staged<12, 19, CH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
+        cudaFuncSetAttribute(k_staged<12, 19, CH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
+        float h1 = time_ms([&] { k_staged<12, 19, CH, false><<<nb / 2, 128, shm>>>(out, nb, N, nnz, 1.0); }, 20);
+        float h2 = time_ms([&] { k_staged<12, 19, CH, true><<<nb / 2, 128, shm>>>(out, nb, N, nnz, 1.0); }, 20);
+        printf("H staged 10 colours, warp stores %.4f ms  %.0f GB/s  (err %s)\n", h1, bytes / h1 / 1e6, cudaGetErrorString(cudaGetLastError()));
+        printf("H staged 10 colours, bulk copies %.4f ms  %.0f GB/s  (err %s)\n", h2, bytes / h2 / 1e6, cudaGetErrorString(cudaGetLastError()));
+    }
     printf("bytes per launch %.1f MB\n", bytes / 1e6);
     printf("A contiguous        %.4f ms  %.0f GB/s\n", a, bytes / a / 1e6);
     printf("B kernel pattern    %.4f ms  %.0f GB/s\n", b, bytes / b / 1e6);
