@@ -738,6 +738,7 @@ int lpb_create(const lpb_problem_desc* desc, lpb_handle** out)
         h->opts.sm_count = prop.multiProcessorCount;
         h->opts.block = 128;
         h->opts.unroll_colours = -1;
+        h->opts.stage_values = 0; // measured slower than the per-thread scatter on B200, kept as an option
         CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         h->own_stream = true;
         build_entry_tables(h->vt->NS, h->eent, h->lent);
@@ -1382,6 +1383,7 @@ int lpb_set_option_int(lpb_handle* h, const char* name, int value)
     }
     else if (!std::strcmp(name, "unroll_colours")) h->opts.unroll_colours = value;
     else if (!std::strcmp(name, "rotate_nodes")) h->opts.no_rotate = value ? 0 : 1;
+    else if (!std::strcmp(name, "stage_values")) h->opts.stage_values = value;
     else if (!std::strcmp(name, "time_kernels")) h->time_kernels = value != 0;
     else throw ApiError(LPB_ERR_INVALID, std::string("unknown option ") + name);
     LPB_API_END(h)

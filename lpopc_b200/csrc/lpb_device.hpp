@@ -93,6 +93,7 @@ struct LaunchOpts {
     int skip_const;     // 1: do not write the constant tail [L | C] of the Jacobian values (the host-pointer
                         // entry points fill it in the caller's array from a cached copy instead of moving it
                         // over PCIe on every call)
+    int stage_values;   // Jacobian kernel: 1 = shared-memory staged write-out where it applies, 0 = per-thread scatter (option "stage_values")
     int no_rotate;      // 1: do not rotate the thread -> node map of the Jacobian kernel (A/B measurement)
     int unroll_colours; // Jacobian kernel variant: -1 = functor default (P::UNROLL_COLOURS), 0 = colour loop, 1 = unrolled
     // optional CUDA events recorded on the launch stream right before / after the dominant
