@@ -124,6 +124,22 @@ __global__ void __launch_bounds__(128) k_staged(double* out, int nb, int N, size
     }
 }
 
+// I: two adjacent nodes per thread, 16-byte stores: a warp writes a whole 512-byte block per instruction
+template <int NROW, int NB>
+__global__ void __launch_bounds__(128) k_pair(double* out, int nb, int N, size_t pitch, double v)
+{
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int half = N / 2;
+    if (gid >= (long long)nb * half) return;
+    const int b = (int)(gid / half);
+    const int k = 2 * (int)(gid - (long long)b * half);
+    double* vb = out + (size_t)b * pitch + k;
+#pragma unroll 1
+    for (int cc = 0; cc < NB; ++cc)
+#pragma unroll
+        for (int i = 0; i < NROW; ++i) __stcs(reinterpret_cast<double2*>(vb + (unsigned)(i * NB + cc) * (unsigned)N), make_double2(v + cc, v));
+}
+
 template <class F>
 float time_ms(F f, int reps)
 {
@@ -183,6 +199,8 @@ int main()
         printf("H staged 10 colours, warp stores %.4f ms  %.0f GB/s  (err %s)\n", h1, bytes / h1 / 1e6, cudaGetErrorString(cudaGetLastError()));
         printf("H staged 10 colours, bulk copies %.4f ms  %.0f GB/s  (err %s)\n", h2, bytes / h2 / 1e6, cudaGetErrorString(cudaGetLastError()));
     }
+    float pi = time_ms([&] { k_pair<12, 19><<<(nb * N / 2 + 127) / 128, 128>>>(out, nb, N, nnz, 1.0); }, 20);
+    printf("I pairs, 16 B stores, colour-major %.4f ms  %.0f GB/s\n", pi, bytes / pi / 1e6);
     printf("bytes per launch %.1f MB\n", bytes / 1e6);
     printf("A contiguous        %.4f ms  %.0f GB/s\n", a, bytes / a / 1e6);
     printf("B kernel pattern    %.4f ms  %.0f GB/s\n", b, bytes / b / 1e6);
