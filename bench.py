@@ -423,19 +423,29 @@ def main():
         ipm = solver.BatchedIPM(ev, tol=1e-6, max_iter=150, var_blocks=solver.interval_blocks(op, ev.n))
         ipm.solve(X0[:8], XL[:8], XU[:8])  # warm-up
         barrier()
+        solve_sampler = ClockSampler(local_rank)
+        solve_sampler.start()
         ts = time.perf_counter()
         res = ipm.solve(X0, XL, XU, chunk=SOLVE_INSTANCES)
+        torch.cuda.synchronize()
+        t_own = time.perf_counter() - ts  # this rank's own solve time (the barrier below waits for the slowest rank)
         barrier()
         t_solve = torch.tensor([time.perf_counter() - ts], dtype=torch.float64, device=dev)
+        per_rank = torch.zeros((world, 2), dtype=torch.float64, device=dev)  # [seconds, lockstep iterations] of every rank
+        per_rank[rank, 0], per_rank[rank, 1] = t_own, float(res["iters"].max().item())
+        solve_clocks = solve_sampler.stop()
         n_ok = (res["status"] == 0).sum().to(torch.float64).reshape(1)
         it_sum = res["iters"].sum().to(torch.float64).reshape(1)
         if world > 1:
             dist.all_reduce(t_solve, op=dist.ReduceOp.MAX)
             dist.all_reduce(n_ok, op=dist.ReduceOp.SUM)
             dist.all_reduce(it_sum, op=dist.ReduceOp.SUM)
+            dist.all_reduce(per_rank, op=dist.ReduceOp.SUM)
         solves = {"metric": "batched OCP solves/s", "value": float(n_ok.item()) / float(t_solve.item()), "unit": "solves/s",
                   "instances": ns_ * world, "converged": int(n_ok.item()), "seconds": float(t_solve.item()),
                   "iters_mean": float(it_sum.item()) / (ns_ * world), "tol": 1e-6, "nnz_h_probed": ev.nnz_h,
+                  "clocks_rank0": {k: solve_clocks.get(k) for k in ("sm_mhz", "sm_max_mhz", "reasons")},
+                  "seconds_per_rank": [round(v, 3) for v in per_rank[:, 0].tolist()], "iters_max_per_rank": [int(v) for v in per_rank[:, 1].tolist()],
                   "solver": "lockstep primal-dual interior point, exact FD Hessian, KKT step: %s (torch.linalg batched Cholesky / "
                             "triangular solves); NLP callbacks = device-resident transcription kernels" % ipm.kkt_kind}
         del g2, ev, ipm, res

@@ -176,6 +176,15 @@ int lpb_eval_h_dev(lpb_handle* h, int nbatch, const double* d_x, const double* d
 int lpb_structure_dev(lpb_handle* h, const int** d_jac_iRow, const int** d_jac_jCol,
                       const int** d_h_iRow, const int** d_h_jCol);
 
+/* ---- linear algebra of the batched outer solver (lpopc_b200/solver.py) ----
+ * One launch for a whole batched block-tridiagonal solve: B instances, K diagonal Cholesky factors L[i]
+ * ([B][nb][nb] row-major, lower triangle) and K-1 boundary-row couplings C[i] ([B][nbd][nb]) with the boundary
+ * slots bnd[nbd]; rhs/out [B][K][nb].  L and C are HOST arrays of device pointers, everything else device
+ * pointers; asynchronous on `cuda_stream`.  Returns 0, -1 if the shape is not supported (caller falls back to
+ * library solves), or a CUDA error code - 1000. */
+int lpb_blocktri_solve(int B, int K, int nb, int nbd, const double* const* L, const double* const* C, const int* bnd,
+                       const double* rhs, double* out, void* cuda_stream);
+
 /* Tuning / introspection (not part of the reference boundary). */
 int lpb_set_option_int(lpb_handle* h, const char* name, int value);
 long long lpb_kernel_launch_count(const lpb_handle* h); /* kernels launched so far */

@@ -227,8 +227,9 @@ class BlockTridiagKKT:
     residual.  Positive definiteness of H + gamma J^T J is again the inertia test (Debreu), driving the
     per-instance dw."""
 
-    def __init__(self, ipm, blk_free, gamma=1e6, refine=3):
+    def __init__(self, ipm, blk_free, gamma=1e6, refine=3, fused=True):
         self.ipm, self.gamma, self.refine = ipm, gamma, refine
+        self.fused_solve = None if fused else False  # None: not probed yet, True: lpb_blocktri_solve, False: library triangular solves
         ev, dev = ipm.ev, ipm.ev.device
         nf, me = ipm.nf, ipm.me
         K = int(blk_free.max().item()) + 1
@@ -366,7 +367,7 @@ class BlockTridiagKKT:
         for i in range(self.K):
             A = Dp[:, i]
             if i > 0:
-                C = torch.linalg.solve_triangular(prev, Ep[:, i - 1].transpose(1, 2), upper=False).transpose(1, 2)  # E L^-T
+                C = torch.linalg.solve_triangular(prev, Ep[:, i - 1].transpose(1, 2), upper=False).transpose(1, 2).contiguous()  # E L^-T
                 Cs.append(C)
                 A = A.clone()
                 A[:, bi.unsqueeze(1), bi.unsqueeze(0)] -= torch.bmm(C, C.transpose(1, 2))
@@ -378,7 +379,39 @@ class BlockTridiagKKT:
             prev = L
         return Ls, Cs, info
 
+    def _solve_fused(self, Ls, Cs, rb):
+        """The whole forward/backward block substitution in ONE launch (lpb_blocktri_solve, csrc/lpb_blocktri.cu)
+        instead of 2K library triangular solves.  None if the extension or the shape is not available."""
+        if not rb.is_cuda or self.fused_solve is False:
+            return None
+        import ctypes as C
+        if self.fused_solve is None:
+            try:
+                from . import nlp
+                self._lib = nlp.load_library()
+                self._bnd32 = self.bnd.to(torch.int32).contiguous()
+                self.fused_solve = True
+            except Exception:
+                self.fused_solve = False
+                return None
+        B, K, nb = rb.shape
+        rb = rb.contiguous()
+        out = torch.empty_like(rb)
+        Lp = (C.c_void_p * K)(*[L.data_ptr() for L in Ls])
+        Cp = (C.c_void_p * max(K - 1, 1))(*([c.data_ptr() for c in Cs] or [0]))
+        rc = self._lib.lpb_blocktri_solve(B, K, nb, self.nbd, Lp, Cp, C.c_void_p(self._bnd32.data_ptr()), C.c_void_p(rb.data_ptr()),
+                                          C.c_void_p(out.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        if rc == -1:
+            self.fused_solve = False  # shape not supported: library solves from now on
+            return None
+        if rc != 0:
+            raise RuntimeError("lpb_blocktri_solve failed: %d" % rc)
+        return out
+
     def _solve(self, Ls, Cs, rb):
+        fused = self._solve_fused(Ls, Cs, rb)
+        if fused is not None:
+            return fused
         bi = self.bnd
         ys = []
         for i in range(self.K):
@@ -467,11 +500,11 @@ def interval_blocks(op, n_total):
 class BatchedIPM:
     """Lockstep primal-dual interior-point method over a batch of instances of one NLP."""
 
-    def __init__(self, ev, tol=1e-6, max_iter=100, mu0=0.1, rho=1e3, verbose=False, var_blocks=None, kkt_gamma=1e6, kkt_refine=3):
+    def __init__(self, ev, tol=1e-6, max_iter=100, mu0=0.1, rho=1e3, verbose=False, var_blocks=None, kkt_gamma=1e6, kkt_refine=3, kkt_fused=True):
         """var_blocks: optional block id (mesh interval) per NLP variable (`interval_blocks(op, n)`): selects the
         block-tridiagonal KKT step when the problem's coupling allows it, the dense condensed step otherwise."""
         self.var_blocks = var_blocks
-        self.kkt_gamma, self.kkt_refine = kkt_gamma, kkt_refine
+        self.kkt_gamma, self.kkt_refine, self.kkt_fused = kkt_gamma, kkt_refine, kkt_fused
         self.kkt_kind = "dense"
         _, _, gl, gu = ev.bounds()
         self.user_ev = ev
@@ -508,7 +541,7 @@ class BatchedIPM:
         self.kkt_kind = "dense"
         if self.var_blocks is not None:
             try:
-                self.kkt = BlockTridiagKKT(self, self._free_blocks(), gamma=self.kkt_gamma, refine=self.kkt_refine)
+                self.kkt = BlockTridiagKKT(self, self._free_blocks(), gamma=self.kkt_gamma, refine=self.kkt_refine, fused=self.kkt_fused)
                 self.kkt_kind = "block-tridiagonal (K=%d, nb=%d, boundary=%d)" % (self.kkt.K, self.kkt.nb, self.kkt.nbd)
             except ValueError:
                 pass  # coupling does not fit (free phase times, x0-xf Mayer terms, ...): dense step
