@@ -304,7 +304,9 @@ def main():
     op.phases[0].set_mesh(mp, nd)
     g = nlp.TranscribedNLP(op)
     g.set_stream(torch.cuda.current_stream().cuda_stream)
-    g.set_option("host_threads", max(1, min(16, len(os.sched_getaffinity(0)) // world)))  # ranks share the host cores
+    # ranks share the host cores; 8 fill threads saturate the host's write bandwidth (scripts/dev/e2e_probe.py), more only
+    # compete with the driver's own threads
+    g.set_option("host_threads", max(1, min(8, len(os.sched_getaffinity(0)) // world)))
     n, m, nnz, nnz_h = g.get_nlp_info()
     nb = INSTANCES_PER_GPU
     first = rank * nb

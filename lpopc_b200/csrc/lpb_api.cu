@@ -381,7 +381,7 @@ struct lpb_handle {
     DevBuf<double> d_tem, d_abserr, d_conv;
     std::vector<double> h_ctail;
     int host_fill_const = 1; // option "host_fill_const"
-    int host_threads = 0;    // option "host_threads": threads of the constant-tail fill (0 = min(hardware threads, 16))
+    int host_threads = 0;    // option "host_threads": threads of the constant-tail fill (0 = min(hardware threads / 2, 16))
     // sparse return of the head [NL] (k_return_head): segment table of one instance's head, the segments
     // seen non-zero so far, and the host's fill plan (zero runs of the off-segments + the constant tail)
     int sparse_return = 1;   // option "sparse_return"
@@ -1022,7 +1022,7 @@ int lpb_eval_g_jac_batch(lpb_handle* h, int nbatch, const double* x, double* g, 
     std::vector<std::thread> th;
     if (host_tail && !(h->debug_skip & 1)) {
         unsigned hw = std::thread::hardware_concurrency();
-        int nt = (int)(hw ? hw : 1);
+        int nt = (int)(hw > 1 ? hw / 2 : 1); // half the hardware threads: the rest is left to the driver and the caller
         if (nt > 16) nt = 16;
         if (h->host_threads > 0) nt = h->host_threads;
         if ((size_t)nbatch * tail < (size_t)1 << 16) nt = 1;
