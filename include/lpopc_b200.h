@@ -160,7 +160,11 @@ int lpb_eval_g_jac_batch(lpb_handle* h, int nbatch, const double* x, double* g, 
  * non-zero are sent by the GPU (zero-copy stores); the all-zero segments of the reference's forced-dense
  * pattern are verified on the device on every call and written as zeros by the host threads (a segment
  * that turns non-zero is fetched afterwards, so the caller always gets the exact device values).
- * Options "sparse_return" (default 1), "host_fill_const" (1), "host_threads" (0 = auto). */
+ * Options "sparse_return" (default 1), "host_fill_const" (1), "host_threads" (0 = auto).
+ * Option "auto_pin" (default 0): page-lock large PAGEABLE caller arrays (x, g, values, lambda, grad) that come
+ * back with the same address on a second call, as IPOPT's do -- a pageable array is copied through a staging
+ * buffer at a few GB/s, a page-locked one moves at PCIe speed and is eligible for the sparse return.  The caller
+ * must keep such arrays alive until lpb_destroy or until the option is set back to 0 (which releases them). */
 int lpb_eval_h_batch(lpb_handle* h, int nbatch, const double* x, const double* obj_factor,
                      const double* lambda, double* values);
 
@@ -190,7 +194,7 @@ int lpb_set_option_int(lpb_handle* h, const char* name, int value);
 long long lpb_kernel_launch_count(const lpb_handle* h); /* kernels launched so far */
 /* Counters: "sparse_calls" (host-pointer calls that used the sparse return), "sparse_fixups" (segments fetched
  * after a wrong all-zero prediction), "sparse_on_doubles" (values per instance that cross PCIe on that path),
- * "head_doubles" (size of [NL] per instance). */
+ * "head_doubles" (size of [NL] per instance), "pinned_buffers" (caller arrays page-locked by "auto_pin"). */
 int lpb_get_stat(lpb_handle* h, const char* name, long long* value);
 /* With option "time_kernels" = 1 every evaluation brackets its dominant node kernel
  * ("cons_jac": k_cons_jac, "hess_nodes": k_hess_nodes) with CUDA events on the handle's

@@ -385,6 +385,13 @@ struct lpb_handle {
     // sparse return of the head [NL] (k_return_head): segment table of one instance's head, the segments
     // seen non-zero so far, and the host's fill plan (zero runs of the off-segments + the constant tail)
     int sparse_return = 1;   // option "sparse_return"
+    // option "auto_pin": page-lock (cudaHostRegister) large pageable caller arrays that come back with the same
+    // address and size on a second call -- IPOPT hands the same x / g / values arrays to every callback, and a
+    // pageable array costs a staged copy at ~6 GB/s instead of a DMA at PCIe speed.  Off by default: the caller
+    // must keep such arrays alive until lpb_destroy (or lpb_unpin_host_buffers).
+    int auto_pin = 0;
+    struct HostBuf { const void* p; size_t bytes; bool pinned; };
+    std::vector<HostBuf> host_bufs;
     int debug_skip = 0;      // option "debug_skip" (measurement only): 1 = no host fill, 2 = no return of the head
     std::vector<int> seg_off, seg_len;
     std::vector<unsigned char> seg_on, seg_maskable;
@@ -406,6 +413,9 @@ struct lpb_handle {
         if (own_stream && stream) cudaStreamDestroy(stream);
         for (cudaStream_t p : pipe) if (p) cudaStreamDestroy(p);
         if (h_seg_flags) cudaFreeHost(h_seg_flags);
+        for (auto& hb : host_bufs)
+            if (hb.pinned) cudaHostUnregister(const_cast<void*>(hb.p));
+        cudaGetLastError();
     }
 };
 
@@ -909,6 +919,25 @@ int lpb_structure_dev(lpb_handle* h, const int** d_jac_iRow, const int** d_jac_j
 }
 
 // ---- host-pointer entry points (TNLP-style) ---------------------------------------------------
+// option "auto_pin": see lpb_handle::auto_pin
+static void maybe_pin(lpb_handle* h, const void* p, size_t bytes)
+{
+    if (!h->auto_pin || !p || bytes < ((size_t)1 << 20)) return;
+    for (auto& hb : h->host_bufs) {
+        if (hb.p != p) continue;
+        if (hb.pinned && hb.bytes >= bytes) return;
+        if (hb.pinned) { cudaHostUnregister(const_cast<void*>(p)); hb.pinned = false; } // grown: register the larger range
+        cudaPointerAttributes at;
+        const bool pageable = cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type == cudaMemoryTypeUnregistered;
+        cudaGetLastError();
+        hb.bytes = bytes;
+        if (pageable && cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterMapped | cudaHostRegisterPortable) == cudaSuccess) hb.pinned = true;
+        else cudaGetLastError(); // cannot be registered (read-only mapping, limits, ...): stay with staged copies
+        return;
+    }
+    if (h->host_bufs.size() < 64) h->host_bufs.push_back({p, bytes, false}); // first sighting: pin when it comes back
+}
+
 static void h2d(lpb_handle* h, DevBuf<double>& buf, const double* src, size_t n)
 {
     buf.reserve(n);
@@ -938,6 +967,8 @@ int lpb_eval_grad_f_batch(lpb_handle* h, int nbatch, const double* x, double* gr
     LPB_API_BEGIN(h)
     need_fresh(h);
     if (nbatch < 1 || !x || !grad_f) throw ApiError(LPB_ERR_INVALID, "bad argument");
+    maybe_pin(h, x, (size_t)nbatch * h->pd.n * sizeof(double));
+    maybe_pin(h, grad_f, (size_t)nbatch * h->pd.n * sizeof(double));
     h2d(h, h->d_x, x, (size_t)nbatch * h->pd.n);
     h->d_grad.reserve((size_t)nbatch * h->pd.n);
     int rc = lpb_eval_grad_f_dev(h, nbatch, h->d_x.p, h->d_grad.p);
@@ -1001,6 +1032,9 @@ int lpb_eval_g_jac_batch(lpb_handle* h, int nbatch, const double* x, double* g, 
     h->d_x.reserve((size_t)nbatch * n);
     if (g) h->d_g.reserve((size_t)nbatch * m);
     if (values) h->d_vals.reserve((size_t)nbatch * nnz);
+    maybe_pin(h, x, (size_t)nbatch * n * sizeof(double));
+    maybe_pin(h, g, (size_t)nbatch * m * sizeof(double));
+    maybe_pin(h, values, (size_t)nbatch * nnz * sizeof(double));
     // The tail [L | C] of every instance's values is a constant of the mesh: instead of writing it
     // on the device and moving it over PCIe on every call, host threads copy it from the cached
     // tail into the caller's array while the DMA engine brings back the x-dependent head [NL].
@@ -1124,6 +1158,9 @@ int lpb_eval_h_batch(lpb_handle* h, int nbatch, const double* x, const double* o
     LPB_API_BEGIN(h)
     need_fresh(h);
     if (nbatch < 1 || !x || !obj_factor || !lambda || !values) throw ApiError(LPB_ERR_INVALID, "bad argument");
+    maybe_pin(h, x, (size_t)nbatch * h->pd.n * sizeof(double));
+    maybe_pin(h, lambda, (size_t)nbatch * h->pd.m * sizeof(double));
+    maybe_pin(h, values, (size_t)nbatch * h->pd.nnz_h * sizeof(double));
     h2d(h, h->d_x, x, (size_t)nbatch * h->pd.n);
     h2d(h, h->d_lambda, lambda, (size_t)nbatch * h->pd.m);
     h2d(h, h->d_sigma, obj_factor, (size_t)nbatch);
@@ -1375,6 +1412,15 @@ int lpb_set_option_int(lpb_handle* h, const char* name, int value)
     else if (!std::strcmp(name, "host_threads")) h->host_threads = value;
     else if (!std::strcmp(name, "sparse_return")) h->sparse_return = value;
     else if (!std::strcmp(name, "debug_skip")) h->debug_skip = value;
+    else if (!std::strcmp(name, "auto_pin")) {
+        h->auto_pin = value;
+        if (!value) { // forget (and release) everything that was page-locked on the caller's behalf
+            for (auto& hb : h->host_bufs)
+                if (hb.pinned) cudaHostUnregister(const_cast<void*>(hb.p));
+            cudaGetLastError();
+            h->host_bufs.clear();
+        }
+    }
     else if (!std::strcmp(name, "sparse_forget")) { // test hook: forget every learnt segment (all predicted zero)
         need_fresh(h);
         std::fill(h->seg_on.begin(), h->seg_on.end(), (unsigned char)0);
@@ -1414,6 +1460,11 @@ int lpb_get_stat(lpb_handle* h, const char* name, long long* value)
     else if (!std::strcmp(name, "sparse_fixups")) *value = h->sparse_fixups;
     else if (!std::strcmp(name, "sparse_on_doubles")) *value = h->seg_mask_init ? (long long)h->on_doubles : -1;
     else if (!std::strcmp(name, "head_doubles")) *value = (long long)h->pd.lin_val0;
+    else if (!std::strcmp(name, "pinned_buffers")) {
+        long long c = 0;
+        for (auto& hb : h->host_bufs) c += hb.pinned ? 1 : 0;
+        *value = c;
+    }
     else throw ApiError(LPB_ERR_INVALID, std::string("unknown counter ") + name);
     LPB_API_END(h)
 }

@@ -144,3 +144,31 @@ def test_sparse_return_off_and_mesh_change(nlp_mod):
         g.eval_g_jac_batch_ptr(nb, hx2.data_ptr(), tg2.data_ptr(), tv2.data_ptr())
         assert np.array_equal(_bits(hv2), _bits(d2[1])) and np.array_equal(_bits(hg2), _bits(d2[0]))
     assert g.stat("sparse_calls") == 2
+
+
+def test_auto_pin_registers_reused_pageable_buffers(nlp_mod):
+    """Option auto_pin: pageable caller arrays that come back with the same address are page-locked on the second
+    call (IPOPT reuses its arrays), after which the call takes the DMA / sparse-return path -- results unchanged."""
+    op = cases.build("quadrotor/u8x8")
+    g = nlp_mod.TranscribedNLP(op)
+    n, m, nnz, _ = g.get_nlp_info()
+    nb = 320
+    X = [np.ascontiguousarray(_batch_inputs(op, g, nb, 40 + k)) for k in range(2)]
+    dense = [g.eval_g_jac_batch(x) for x in X]
+    xbuf, gbuf, vbuf = np.empty((nb, n)), np.empty((nb, m)), np.empty((nb, nnz))
+    g.set_option("auto_pin", 1)
+    for k in range(5):
+        xbuf[:] = X[k % 2]
+        gbuf[:] = np.nan
+        vbuf[:] = np.nan
+        g.eval_g_jac_batch(xbuf, gbuf, vbuf)
+        assert np.array_equal(_bits(vbuf), _bits(dense[k % 2][1])) and np.array_equal(_bits(gbuf), _bits(dense[k % 2][0])), k
+        if k == 0:
+            assert g.stat("pinned_buffers") == 0
+        if k >= 1:
+            assert g.stat("pinned_buffers") == 3
+    assert g.stat("sparse_calls") >= 2  # pinned from call 2 on: call 2 learns the segments, calls 3.. are sparse
+    g.set_option("auto_pin", 0)
+    assert g.stat("pinned_buffers") == 0
+    g.eval_g_jac_batch(xbuf, gbuf, vbuf)
+    assert np.array_equal(_bits(vbuf), _bits(dense[0][1]))
