@@ -9,8 +9,7 @@
 //     backward  x_i = L_i^-T (y_i - C_i^T x_{i+1}[bnd])                     i = K-1 .. 0
 // i.e. 2K dependent single-vector triangular solves per instance.  Through the library that is 2K launches whose
 // cost does not shrink with the batch (and grows per matrix for small batches: the straggler tail of the
-// lockstep iteration).  Here ONE launch does the whole solve: one CTA per instance, the factor of the current
-// interval in shared memory (packed lower triangle, nb (nb+1) / 2 doubles), thread i owns row i of the
+// lockstep iteration).  Here ONE launch does the whole solve: one CTA per instance, thread i owns row i of the
 // right-hand side, 32-row panels eliminated with register shuffles and one barrier per panel.
 #include <cuda_runtime.h>
 #include <cstddef>
@@ -29,41 +28,33 @@ struct BlockTriArgs {
     int B, K, nb, nbd;
 };
 
-__device__ __forceinline__ size_t tri(int i) { return (size_t)i * (i + 1) / 2; }
-
-// Substitution by 32-row panels: the warp that owns a panel's rows eliminates the 32 x 32 diagonal block with
-// register shuffles (no barrier inside), publishes the panel's solution in shared memory, and after ONE barrier
-// every remaining row folds the panel in with 32 multiply-adds.  Diagonal reciprocals are taken once per factor.
-__global__ void k_blocktri_solve(const __grid_constant__ BlockTriArgs a)
+// Substitution by 32-row panels, factors read straight from global memory (L2): thread r owns row r of the
+// right-hand side and, per panel, holds the 32 entries of ITS row (forward) or column (backward) of that panel
+// in registers.  The warp that owns the panel's rows eliminates the 32 x 32 diagonal block with register
+// shuffles (no barrier inside), publishes the panel's solution in shared memory, and after ONE barrier every
+// remaining row folds the panel in with 32 multiply-adds (four independent chains).  Shared memory holds only the
+// solution vectors ((K + 1) nb doubles), so occupancy is set by registers, not by a staged factor.
+__global__ void __launch_bounds__(256)
+k_blocktri_solve(const __grid_constant__ BlockTriArgs a)
 {
     extern __shared__ double sm[];
     const int nb = a.nb, nbd = a.nbd, K = a.K;
-    double* Lp = sm;                          // packed lower triangle of the current factor
-    double* ys = Lp + tri(nb);                // [K][nb] forward results
-    double* piv = ys + (size_t)K * nb;        // [nb] right-hand side scratch / backward solution of the current interval
-    double* rd = piv + nb;                    // [nb] reciprocals of the factor's diagonal
+    double* ys = sm;                          // [K][nb] forward results
+    double* piv = ys + (size_t)K * nb;        // [nb, padded to whole panels] right-hand side scratch / backward solution of the current interval
     const int b = blockIdx.x, tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31, nwarp = blockDim.x >> 5;
     const int p0 = warp * 32;                 // first row of this warp's panel (thread = row)
     const unsigned full = 0xffffffffu;
+    const bool live = tid < nb;
+    if (!live) piv[tid] = 0.0; // padding of the last panel: read (times a zero factor entry) by the backward updates
 
-    auto load_factor = [&](int i) {
-        const double* __restrict__ Lg = a.L[i] + (size_t)b * nb * nb;
-        for (int r = warp; r < nb; r += nwarp) // warp per row: coalesced over the row's r + 1 entries
-            for (int c = lane; c <= r; c += 32) {
-                const double v = Lg[(size_t)r * nb + c];
-                Lp[tri(r) + c] = v;
-                if (c == r) rd[r] = 1.0 / v;
-            }
-    };
-
-    // ---- forward ----
+    // ---- forward: L y = r ----
     for (int i = 0; i < K; ++i) {
-        __syncthreads(); // the previous interval's solve has finished with Lp / rd / piv
-        load_factor(i);
-        double t = tid < nb ? a.rhs[((size_t)b * K + i) * nb + tid] : 0.0;
+        const double* __restrict__ Lg = a.L[i] + (size_t)b * nb * nb;
+        const double* __restrict__ Lrow = Lg + (size_t)(live ? tid : 0) * nb;
+        double t = live ? a.rhs[((size_t)b * K + i) * nb + tid] : 0.0;
         if (i > 0) { // r_i[bnd] -= C_{i-1} y_{i-1}: warp per boundary row, coalesced dot product
-            if (tid < nb) piv[tid] = t;
+            if (live) piv[tid] = t;
             __syncthreads();
             const double* __restrict__ Cg = a.C[i - 1] + (size_t)b * nbd * nb;
             const double* __restrict__ yp = ys + (size_t)(i - 1) * nb;
@@ -75,74 +66,93 @@ __global__ void k_blocktri_solve(const __grid_constant__ BlockTriArgs a)
                 if (lane == 0) piv[a.bnd[q]] -= acc;
             }
             __syncthreads();
-            if (tid < nb) t = piv[tid];
-        } else __syncthreads();
+            if (live) t = piv[tid];
+        }
         double* __restrict__ y = ys + (size_t)i * nb;
-        for (int q0 = 0; q0 < nb; q0 += 32) { // panel of columns q0 .. q0 + 31
-            if (p0 == q0) { // owner warp: 32 x 32 diagonal block, forward, in registers
+        for (int q0 = 0; q0 <= p0 && q0 < nb; q0 += 32) { // panels up to and including this warp's own
+            double seg[32]; // L[row][q0 .. q0+31] (entries right of the diagonal are never used)
+#pragma unroll
+            for (int j = 0; j < 32; ++j) seg[j] = (live && q0 + j <= tid) ? Lrow[q0 + j] : 0.0;
+            if (p0 == q0) { // owner warp: 32 x 32 diagonal block in registers
+                double dg = 1.0; // own diagonal entry L[row][row] = seg[lane]
+#pragma unroll
+                for (int j = 0; j < 32; ++j) dg = (lane == j) ? seg[j] : dg;
+                const double rdg = live ? 1.0 / dg : 0.0;
                 double mine = 0.0;
-                const int lim = nb - q0 < 32 ? nb - q0 : 32;
-                for (int j = 0; j < lim; ++j) {
-                    const double yj = __shfl_sync(full, t, j) * rd[q0 + j];
-                    if (lane == j) mine = yj;
-                    if (lane > j && tid < nb) t -= Lp[tri(tid) + q0 + j] * yj;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const double yj = __shfl_sync(full, t, j) * __shfl_sync(full, rdg, j);
+                    mine = (lane == j) ? yj : mine;
+                    if (lane > j) t -= seg[j] * yj;
                 }
-                if (tid < nb) y[tid] = mine;
-            }
-            __syncthreads();
-            if (p0 > q0 && tid < nb) { // rows below the panel
-                const double* __restrict__ row = Lp + tri(tid) + q0;
-                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0; // four independent chains: the update is latency-bound
+                if (live) y[tid] = mine;
+                __syncthreads(); // matches the barrier the lower warps wait at for this panel
+            } else {
+                __syncthreads(); // panel q0 published by its owner
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
-                    s0 += row[j] * y[q0 + j];
-                    s1 += row[j + 1] * y[q0 + j + 1];
-                    s2 += row[j + 2] * y[q0 + j + 2];
-                    s3 += row[j + 3] * y[q0 + j + 3];
+                    s0 += seg[j] * y[q0 + j];
+                    s1 += seg[j + 1] * y[q0 + j + 1];
+                    s2 += seg[j + 2] * y[q0 + j + 2];
+                    s3 += seg[j + 3] * y[q0 + j + 3];
                 }
                 t -= (s0 + s1) + (s2 + s3);
             }
         }
+        // warps above the last panels still owe the barriers of the panels after their own
+        for (int q0 = p0 + 32; q0 < nb; q0 += 32) __syncthreads();
+        __syncthreads(); // y_i complete before the next interval's coupling reads it
     }
-    // ---- backward ----
+    // ---- backward: L^T x = y ----
     for (int i = K - 1; i >= 0; --i) {
-        __syncthreads();
-        if (i != K - 1) load_factor(i); // the last factor is still resident
-        double t = tid < nb ? ys[(size_t)i * nb + tid] : 0.0;
-        if (i + 1 < K && tid < nb) { // y_i -= C_i^T x_{i+1}[bnd]: thread = column, coalesced over columns
+        const double* __restrict__ Lg = a.L[i] + (size_t)b * nb * nb;
+        double t = live ? ys[(size_t)i * nb + tid] : 0.0;
+        if (i + 1 < K && live) { // y_i -= C_i^T x_{i+1}[bnd]: thread = column, coalesced over columns
             const double* __restrict__ Cg = a.C[i] + (size_t)b * nbd * nb;
             const double* __restrict__ xn = a.out + ((size_t)b * K + i + 1) * nb;
             double acc = 0.0;
             for (int q = 0; q < nbd; ++q) acc += Cg[(size_t)q * nb + tid] * xn[a.bnd[q]];
             t -= acc;
         }
-        __syncthreads();
-        for (int q0 = (nb - 1) / 32 * 32; q0 >= 0; q0 -= 32) { // L^T x = t, panels from the last to the first
-            if (p0 == q0) {
-                double mine = 0.0;
-                const int lim = nb - q0 < 32 ? nb - q0 : 32;
-                for (int j = lim - 1; j >= 0; --j) {
-                    const double xj = __shfl_sync(full, t, j) * rd[q0 + j];
-                    if (lane == j) mine = xj;
-                    if (lane < j) t -= Lp[tri(q0 + j) + tid] * xj; // L^T(tid, q0+j) = L(q0+j, tid): contiguous in the packed row
-                }
-                if (tid < nb) piv[tid] = mine;
+        const int qlast = (nb - 1) / 32 * 32;
+        for (int q0 = qlast; q0 > p0; q0 -= 32) { // panels after this warp's own: fold them in
+            double seg[32]; // L[q0+j][tid], j = 0..31: column tid of the panel's rows, coalesced over tid
+#pragma unroll
+            for (int j = 0; j < 32; ++j) seg[j] = (live && q0 + j < nb) ? Lg[(size_t)(q0 + j) * nb + tid] : 0.0;
+            __syncthreads(); // panel q0 published by its owner
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                s0 += seg[j] * piv[q0 + j];
+                s1 += seg[j + 1] * piv[q0 + j + 1];
+                s2 += seg[j + 2] * piv[q0 + j + 2];
+                s3 += seg[j + 3] * piv[q0 + j + 3];
             }
-            __syncthreads();
-            if (p0 < q0) { // rows above the panel
-                const int lim = nb - q0 < 32 ? nb - q0 : 32;
-                double s0 = 0.0, s1 = 0.0;
-                int j = 0;
-                for (; j + 1 < lim; j += 2) {
-                    s0 += Lp[tri(q0 + j) + tid] * piv[q0 + j];
-                    s1 += Lp[tri(q0 + j + 1) + tid] * piv[q0 + j + 1];
-                }
-                if (j < lim) s0 += Lp[tri(q0 + j) + tid] * piv[q0 + j];
-                t -= s0 + s1;
-            }
+            t -= (s0 + s1) + (s2 + s3);
         }
-        if (tid < nb) a.out[((size_t)b * K + i) * nb + tid] = piv[tid];
+        if (p0 < nb) { // own panel: diagonal block of L^T, backward, in registers
+            double seg[32]; // L[p0+j][tid] for j >= lane
+#pragma unroll
+            for (int j = 0; j < 32; ++j) seg[j] = (live && p0 + j < nb && j >= lane) ? Lg[(size_t)(p0 + j) * nb + tid] : 0.0;
+            double dg = 1.0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) dg = (lane == j) ? seg[j] : dg;
+            const double rdg = live ? 1.0 / dg : 0.0;
+            double mine = 0.0;
+#pragma unroll
+            for (int j = 31; j >= 0; --j) {
+                const double xj = __shfl_sync(full, t, j) * __shfl_sync(full, rdg, j);
+                mine = (lane == j) ? xj : mine;
+                if (lane < j) t -= seg[j] * xj;
+            }
+            if (live) piv[tid] = mine;
+        }
+        __syncthreads(); // own panel published
+        for (int q0 = p0 - 32; q0 >= 0; q0 -= 32) __syncthreads(); // the barriers of the panels before this warp's own
+        if (live) a.out[((size_t)b * K + i) * nb + tid] = piv[tid];
         __threadfence_block();
+        __syncthreads(); // x_i visible to the block (next interval's coupling) and piv free for reuse
     }
 }
 
@@ -151,14 +161,14 @@ __global__ void k_blocktri_solve(const __grid_constant__ BlockTriArgs a)
 extern "C" {
 
 // Device pointers throughout; asynchronous on `stream`.  Returns 0, -1 (shape not supported: K > 64 or the
-// packed factor does not fit in shared memory -- the caller falls back to library solves) or a negative
+// nb > 256 -- the caller falls back to library solves) or a negative
 // cudaError_t - 1000.
 int lpb_blocktri_solve(int B, int K, int nb, int nbd, const double* const* L, const double* const* C, const int* bnd,
                        const double* rhs, double* out, void* stream)
 {
     if (B < 1 || K < 1 || K > kMaxBlocks || nb < 1 || nbd < 0) return -1;
-    const size_t shm = ((size_t)nb * (nb + 1) / 2 + (size_t)K * nb + 2 * (size_t)nb) * sizeof(double);
-    if (shm > 220 * 1024 || nb > 1024) return -1;
+    const size_t shm = ((size_t)K * nb + (size_t)(nb + 31) / 32 * 32) * sizeof(double); // piv padded to whole panels
+    if (shm > 200 * 1024 || nb > 256) return -1;
     BlockTriArgs a;
     for (int i = 0; i < K; ++i) a.L[i] = L[i];
     for (int i = 0; i + 1 < K; ++i) a.C[i] = C[i];
