@@ -181,13 +181,19 @@ int lpb_structure_dev(lpb_handle* h, const int** d_jac_iRow, const int** d_jac_j
                       const int** d_h_iRow, const int** d_h_jCol);
 
 /* ---- linear algebra of the batched outer solver (lpopc_b200/solver.py) ----
- * One launch for a whole batched block-tridiagonal solve: B instances, K diagonal Cholesky factors L[i]
- * ([B][nb][nb] row-major, lower triangle) and K-1 boundary-row couplings C[i] ([B][nbd][nb]) with the boundary
- * slots bnd[nbd]; rhs/out [B][K][nb].  L and C are HOST arrays of device pointers, everything else device
- * pointers; asynchronous on `cuda_stream`.  Returns 0, -1 if the shape is not supported (caller falls back to
- * library solves), or a CUDA error code - 1000. */
-int lpb_blocktri_solve(int B, int K, int nb, int nbd, const double* const* L, const double* const* C, const int* bnd,
-                       const double* rhs, double* out, void* cuda_stream);
+ * Batched block-tridiagonal positive definite systems over the mesh intervals: B instances, K diagonal blocks of
+ * nb x nb, off-diagonal coupling only through the nbd boundary slots bnd[] (ascending) of the next block.
+ * lpb_blocktri_factor: Dp [B][K][nb][nb] (symmetric, lower triangle read), Ep [B][K-1][nbd][nb] ->
+ *   L (like Dp, lower triangles), C = E L^-T (like Ep), info[B] (0, or 1 + index of the first non-positive pivot:
+ *   the caller's inertia test).  One launch, one CTA per instance.
+ * lpb_blocktri_solve: one launch for the whole forward/backward substitution; L and C are HOST arrays of K and
+ *   K-1 device pointers with instance strides strideL / strideC (doubles); rhs/out [B][K][nb].
+ * Everything else is a device pointer; asynchronous on `cuda_stream`.  Return 0, -1 if the shape is not
+ * supported (caller falls back to library routines), or a CUDA error code - 1000. */
+int lpb_blocktri_factor(int B, int K, int nb, int nbd, const double* Dp, const double* Ep, const int* bnd, double* L, double* C,
+                        int* info, void* cuda_stream);
+int lpb_blocktri_solve(int B, int K, int nb, int nbd, const double* const* L, const double* const* C, long long strideL,
+                       long long strideC, const int* bnd, const double* rhs, double* out, void* cuda_stream);
 
 /* Tuning / introspection (not part of the reference boundary). */
 int lpb_set_option_int(lpb_handle* h, const char* name, int value);

@@ -20,11 +20,12 @@ namespace {
 constexpr int kMaxBlocks = 64;
 
 struct BlockTriArgs {
-    const double* L[kMaxBlocks]; // K factors, each [B][nb][nb] row-major (lower triangle read)
-    const double* C[kMaxBlocks]; // K-1 couplings, each [B][nbd][nb] row-major
+    const double* L[kMaxBlocks]; // K factors, each [B][nb][nb] row-major with instance stride sL (lower triangle read)
+    const double* C[kMaxBlocks]; // K-1 couplings, each [B][nbd][nb] row-major with instance stride sC
     const int* bnd;              // [nbd] boundary slots of a block
     const double* rhs;           // [B][K][nb]
     double* out;                 // [B][K][nb]
+    long long sL, sC;            // doubles between consecutive instances of one factor / coupling
     int B, K, nb, nbd;
 };
 
@@ -50,13 +51,13 @@ k_blocktri_solve(const __grid_constant__ BlockTriArgs a)
 
     // ---- forward: L y = r ----
     for (int i = 0; i < K; ++i) {
-        const double* __restrict__ Lg = a.L[i] + (size_t)b * nb * nb;
+        const double* __restrict__ Lg = a.L[i] + (size_t)b * a.sL;
         const double* __restrict__ Lrow = Lg + (size_t)(live ? tid : 0) * nb;
         double t = live ? a.rhs[((size_t)b * K + i) * nb + tid] : 0.0;
         if (i > 0) { // r_i[bnd] -= C_{i-1} y_{i-1}: warp per boundary row, coalesced dot product
             if (live) piv[tid] = t;
             __syncthreads();
-            const double* __restrict__ Cg = a.C[i - 1] + (size_t)b * nbd * nb;
+            const double* __restrict__ Cg = a.C[i - 1] + (size_t)b * a.sC;
             const double* __restrict__ yp = ys + (size_t)(i - 1) * nb;
             for (int q = warp; q < nbd; q += nwarp) {
                 double acc = 0.0;
@@ -106,10 +107,10 @@ k_blocktri_solve(const __grid_constant__ BlockTriArgs a)
     }
     // ---- backward: L^T x = y ----
     for (int i = K - 1; i >= 0; --i) {
-        const double* __restrict__ Lg = a.L[i] + (size_t)b * nb * nb;
+        const double* __restrict__ Lg = a.L[i] + (size_t)b * a.sL;
         double t = live ? ys[(size_t)i * nb + tid] : 0.0;
         if (i + 1 < K && live) { // y_i -= C_i^T x_{i+1}[bnd]: thread = column, coalesced over columns
-            const double* __restrict__ Cg = a.C[i] + (size_t)b * nbd * nb;
+            const double* __restrict__ Cg = a.C[i] + (size_t)b * a.sC;
             const double* __restrict__ xn = a.out + ((size_t)b * K + i + 1) * nb;
             double acc = 0.0;
             for (int q = 0; q < nbd; ++q) acc += Cg[(size_t)q * nb + tid] * xn[a.bnd[q]];
@@ -156,15 +157,134 @@ k_blocktri_solve(const __grid_constant__ BlockTriArgs a)
     }
 }
 
+
+// ---- factorisation -----------------------------------------------------------------------------------------
+// Block-tridiagonal Cholesky with boundary-row couplings, one CTA per instance, intervals in sequence:
+//     A_i  = Dp_i - scatter_bnd(C_{i-1} C_{i-1}^T)      (packed lower triangle in shared memory)
+//     L_i  = chol(A_i)                                   (right-looking, thread = row, two barriers per column)
+//     C_i  = E_i L_i^-T                                  (nbd right-hand sides, forward substitution in shared memory)
+// info[b] = 0, or 1 + the global index of the first non-positive pivot (the inertia test of the caller: the
+// factor exists iff the regularised matrix is positive definite); after a failure the remaining factors of the
+// instance are set to the identity and its couplings to zero so that the solve stays finite.
+struct FactorArgs {
+    const double* Dp;   // [B][K][nb][nb] symmetric blocks (lower triangle read)
+    const double* Ep;   // [B][K-1][nbd][nb]
+    double* L;          // [B][K][nb][nb] (lower triangle written)
+    double* C;          // [B][K-1][nbd][nb]
+    int* info;          // [B]
+    const int* bnd;     // [nbd], ascending
+    int B, K, nb, nbd;
+};
+
+__device__ __forceinline__ size_t tri(int i) { return (size_t)i * (i + 1) / 2; }
+
+__global__ void __launch_bounds__(256)
+k_blocktri_factor(const __grid_constant__ FactorArgs a)
+{
+    extern __shared__ double sm[];
+    const int nb = a.nb, nbd = a.nbd, K = a.K;
+    double* A = sm;                        // packed lower triangle
+    double* Cs = A + tri(nb);              // [nbd][nb] coupling of the previous / current interval
+    double* z = Cs + (size_t)nbd * nb;     // [nbd] pivots of the coupling substitution
+    double* col = z + nbd;                 // [nb] the scaled column being eliminated (own array: lets the update loops pipeline)
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31, nwarp = blockDim.x >> 5;
+    const bool live = tid < nb;
+    int fail = 0;
+    for (int i = 0; i < K; ++i) {
+        const double* __restrict__ Dg = a.Dp + ((size_t)b * K + i) * nb * nb;
+        double* __restrict__ Lg = a.L + ((size_t)b * K + i) * nb * nb;
+        if (fail) { // identity factor, zero coupling
+            for (int r = warp; r < nb; r += nwarp)
+                for (int c = lane; c <= r; c += 32) Lg[(size_t)r * nb + c] = (r == c) ? 1.0 : 0.0;
+            if (i + 1 < K) {
+                double* __restrict__ Cg = a.C + ((size_t)b * (K - 1) + i) * nbd * nb;
+                for (int e = tid; e < nbd * nb; e += blockDim.x) Cg[e] = 0.0;
+            }
+            continue;
+        }
+        for (int r = warp; r < nb; r += nwarp)
+            for (int c = lane; c <= r; c += 32) A[tri(r) + c] = Dg[(size_t)r * nb + c];
+        __syncthreads();
+        if (i > 0) { // A[bnd, bnd] -= C C^T (lower part; bnd ascending)
+            for (int e = tid; e < nbd * (nbd + 1) / 2; e += blockDim.x) {
+                int q1 = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+                while (tri(q1 + 1) <= (size_t)e) ++q1;
+                while (tri(q1) > (size_t)e) --q1;
+                const int q2 = e - (int)tri(q1);
+                const double* c1 = Cs + (size_t)q1 * nb;
+                const double* c2 = Cs + (size_t)q2 * nb;
+                double s0 = 0.0, s1 = 0.0;
+                int c = 0;
+                for (; c + 1 < nb; c += 2) { s0 += c1[c] * c2[c]; s1 += c1[c + 1] * c2[c + 1]; }
+                if (c < nb) s0 += c1[c] * c2[c];
+                A[tri(a.bnd[q1]) + a.bnd[q2]] -= s0 + s1;
+            }
+            __syncthreads();
+        }
+        // right-looking Cholesky
+        for (int j = 0; j < nb; ++j) {
+            const double ajj = A[tri(j) + j];
+            if (!(ajj > 0.0)) { fail = i * nb + j + 1; break; } // uniform: every thread reads the same pivot
+            const double ljj = sqrt(ajj);
+            double lrj = 0.0;
+            if (live && tid > j) { lrj = A[tri(tid) + j] / ljj; A[tri(tid) + j] = lrj; col[tid] = lrj; }
+            __syncthreads(); // column j scaled (the pivot itself is rewritten below, nobody reads it again as A_jj)
+            if (tid == j) A[tri(j) + j] = ljj;
+            if (live && tid > j) {
+                double* __restrict__ row = A + tri(tid);
+                const double* __restrict__ cj = col;
+#pragma unroll 4
+                for (int c = j + 1; c <= tid; ++c) row[c] -= lrj * cj[c];
+            }
+            __syncthreads();
+        }
+        if (fail) { // this interval failed: hand out the identity for it and everything after
+            if (tid == 0) a.info[b] = fail;
+            __syncthreads();
+            --i; // redo interval i through the identity branch
+            continue;
+        }
+        for (int r = warp; r < nb; r += nwarp)
+            for (int c = lane; c <= r; c += 32) Lg[(size_t)r * nb + c] = A[tri(r) + c];
+        if (i + 1 < K) { // C_i = E_i L_i^-T: solve L z_q = e_q for the nbd rows e_q of E_i, in place in Cs
+            const double* __restrict__ Eg = a.Ep + ((size_t)b * (K - 1) + i) * nbd * nb;
+            for (int e = tid; e < nbd * nb; e += blockDim.x) Cs[e] = Eg[e];
+            __syncthreads();
+            for (int j = 0; j < nb; ++j) {
+                if (tid < nbd) {
+                    const double v = Cs[(size_t)tid * nb + j] / A[tri(j) + j];
+                    Cs[(size_t)tid * nb + j] = v;
+                    z[tid] = v;
+                }
+                __syncthreads();
+                if (live && tid > j) {
+                    const double lrj = A[tri(tid) + j];
+                    double* __restrict__ cr = Cs + tid;
+                    const double* __restrict__ zq = z;
+#pragma unroll 4
+                    for (int q = 0; q < nbd; ++q) cr[(size_t)q * nb] -= lrj * zq[q];
+                }
+                __syncthreads();
+            }
+            double* __restrict__ Cg = a.C + ((size_t)b * (K - 1) + i) * nbd * nb;
+            for (int e = tid; e < nbd * nb; e += blockDim.x) Cg[e] = Cs[e];
+        }
+        __syncthreads();
+    }
+    if (!fail && tid == 0) a.info[b] = 0;
+}
+
 } // namespace
 
 extern "C" {
 
-// Device pointers throughout; asynchronous on `stream`.  Returns 0, -1 (shape not supported: K > 64 or the
-// nb > 256 -- the caller falls back to library solves) or a negative
-// cudaError_t - 1000.
-int lpb_blocktri_solve(int B, int K, int nb, int nbd, const double* const* L, const double* const* C, const int* bnd,
-                       const double* rhs, double* out, void* stream)
+// Device pointers throughout; asynchronous on `stream`.  Returns 0, -1 (shape not supported: K > 64 or
+// nb > 256 -- the caller falls back to library solves) or a negative cudaError_t - 1000.
+// strideL / strideC: doubles between consecutive instances of one factor / coupling (nb*nb and nbd*nb for
+// separately allocated [B][nb][nb] tensors, K*nb*nb and (K-1)*nbd*nb for slices of one [B][K][..] tensor).
+int lpb_blocktri_solve(int B, int K, int nb, int nbd, const double* const* L, const double* const* C, long long strideL, long long strideC,
+                       const int* bnd, const double* rhs, double* out, void* stream)
 {
     if (B < 1 || K < 1 || K > kMaxBlocks || nb < 1 || nbd < 0) return -1;
     const size_t shm = ((size_t)K * nb + (size_t)(nb + 31) / 32 * 32) * sizeof(double); // piv padded to whole panels
@@ -172,7 +292,7 @@ int lpb_blocktri_solve(int B, int K, int nb, int nbd, const double* const* L, co
     BlockTriArgs a;
     for (int i = 0; i < K; ++i) a.L[i] = L[i];
     for (int i = 0; i + 1 < K; ++i) a.C[i] = C[i];
-    a.bnd = bnd; a.rhs = rhs; a.out = out; a.B = B; a.K = K; a.nb = nb; a.nbd = nbd;
+    a.bnd = bnd; a.rhs = rhs; a.out = out; a.sL = strideL; a.sC = strideC; a.B = B; a.K = K; a.nb = nb; a.nbd = nbd;
     static size_t attr = 0;
     if (shm > attr) {
         cudaError_t e = cudaFuncSetAttribute(k_blocktri_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
@@ -181,6 +301,29 @@ int lpb_blocktri_solve(int B, int K, int nb, int nbd, const double* const* L, co
     }
     const int threads = (nb + 31) / 32 * 32;
     k_blocktri_solve<<<B, threads, shm, (cudaStream_t)stream>>>(a);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : -(int)e - 1000;
+}
+
+// Block-tridiagonal Cholesky (k_blocktri_factor above).  Dp [B][K][nb][nb], Ep [B][K-1][nbd][nb] in; L (same
+// shape as Dp, lower triangles), C (same shape as Ep) and info [B] out; bnd ascending.  Same return convention.
+int lpb_blocktri_factor(int B, int K, int nb, int nbd, const double* Dp, const double* Ep, const int* bnd, double* L, double* C, int* info,
+                        void* stream)
+{
+    if (B < 1 || K < 1 || nb < 1 || nbd < 0 || nb > 256) return -1;
+    const size_t shm = ((size_t)nb * (nb + 1) / 2 + (size_t)nbd * nb + (size_t)nbd + (size_t)nb + 2) * sizeof(double);
+    if (shm > 220 * 1024) return -1;
+    FactorArgs a;
+    a.Dp = Dp; a.Ep = Ep; a.L = L; a.C = C; a.info = info; a.bnd = bnd; a.B = B; a.K = K; a.nb = nb; a.nbd = nbd;
+    static size_t attr = 0;
+    if (shm > attr) {
+        cudaError_t e = cudaFuncSetAttribute(k_blocktri_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
+        if (e != cudaSuccess) return -(int)e - 1000;
+        attr = shm;
+    }
+    const int need = nb > nbd ? nb : nbd;
+    const int threads = (need + 31) / 32 * 32;
+    k_blocktri_factor<<<B, threads, shm, (cudaStream_t)stream>>>(a);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : -(int)e - 1000;
 }

@@ -229,6 +229,11 @@ class BlockTridiagKKT:
 
     def __init__(self, ipm, blk_free, gamma=1e6, refine=3, fused=True):
         self.ipm, self.gamma, self.refine = ipm, gamma, refine
+        # lpb_blocktri_factor (one launch, factor in shared memory) beats the library recursion for small blocks
+        # (nb = 44: 1.8 vs 3.5 ms per 4096-instance factorisation) and loses for large ones (nb = 140: 56 vs 29 ms,
+        # scripts/dev/blocktri_probe.py): the column-by-column update is latency-bound at 5 warps per CTA
+        self.fused_factor = bool(fused)  # narrowed to nb <= 64 once the block size is known (below)
+        self.n_factor = self.n_solve = 0  # factorisations / block-tridiagonal solves so far
         self.fused_solve = None if fused else False  # None: not probed yet, True: lpb_blocktri_solve, False: library triangular solves
         ev, dev = ipm.ev, ipm.ev.device
         nf, me = ipm.nf, ipm.me
@@ -242,6 +247,7 @@ class BlockTridiagKKT:
         pos[order] = torch.arange(nf, device=dev) - starts[blk_free[order]]
         nb = int(counts.max().item())
         self.nb = nb
+        self.fused_factor = self.fused_factor and nb <= 64
         self.fpos = blk_free * nb + pos                      # free variable -> slot in the padded [K*nb] layout
         # Jacobian rows: group = lowest block among the row's free columns
         colmap = torch.full((ipm.n,), -1, dtype=torch.int64, device=dev)
@@ -356,9 +362,40 @@ class BlockTridiagKKT:
             out[:, :-1] += torch.einsum("bkij,bki->bkj", E, xb[:, 1:, self.bnd])
         return out
 
+    def _factor_fused(self, Dp, Ep):
+        """The whole block-tridiagonal Cholesky in ONE launch (lpb_blocktri_factor).  None if not available."""
+        if not Dp.is_cuda or self.fused_solve is False:
+            return None
+        import ctypes as C
+        if self.fused_solve is None:
+            try:
+                from . import nlp
+                self._lib = nlp.load_library()
+                self._bnd32 = self.bnd.to(torch.int32).contiguous()
+                self.fused_solve = True
+            except Exception:
+                self.fused_solve = False
+                return None
+        B, K, nb, _ = Dp.shape
+        Dp, Ep = Dp.contiguous(), Ep.contiguous()
+        Lall, Call = torch.empty_like(Dp), torch.empty_like(Ep)
+        info = torch.empty(B, dtype=torch.int32, device=Dp.device)
+        rc = self._lib.lpb_blocktri_factor(B, K, nb, self.nbd, C.c_void_p(Dp.data_ptr()), C.c_void_p(Ep.data_ptr()), C.c_void_p(self._bnd32.data_ptr()),
+                                           C.c_void_p(Lall.data_ptr()), C.c_void_p(Call.data_ptr()), C.c_void_p(info.data_ptr()),
+                                           C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        if rc == -1:
+            return None
+        if rc != 0:
+            raise RuntimeError("lpb_blocktri_factor failed: %d" % rc)
+        return [Lall[:, i] for i in range(K)], [Call[:, i] for i in range(K - 1)], info
+
     def _factor(self, Dp, Ep):
         """Block-tridiagonal Cholesky with boundary-row off-diagonal blocks: L_i L_i^T = A_i - (C_i C_i^T on the
         boundary slots), C_i = E_i L_{i-1}^-T [nbd x nb].  Returns (list L_i, list C_i, info)."""
+        self.n_factor += 1
+        fused = self._factor_fused(Dp, Ep) if self.fused_factor else None
+        if fused is not None:
+            return fused
         Ls, Cs = [], []
         info = torch.zeros(Dp.shape[0], dtype=torch.int32, device=Dp.device)
         eye = torch.eye(self.nb, dtype=torch.float64, device=Dp.device)
@@ -399,7 +436,12 @@ class BlockTridiagKKT:
         out = torch.empty_like(rb)
         Lp = (C.c_void_p * K)(*[L.data_ptr() for L in Ls])
         Cp = (C.c_void_p * max(K - 1, 1))(*([c.data_ptr() for c in Cs] or [0]))
-        rc = self._lib.lpb_blocktri_solve(B, K, nb, self.nbd, Lp, Cp, C.c_void_p(self._bnd32.data_ptr()), C.c_void_p(rb.data_ptr()),
+        sL = Ls[0].stride(0)
+        sC = Cs[0].stride(0) if Cs else 0
+        if any(L.stride(0) != sL or L.stride(1) != nb or L.stride(2) != 1 for L in Ls) or \
+                any(c.stride(0) != sC or c.stride(1) != nb or c.stride(2) != 1 for c in Cs):
+            return None
+        rc = self._lib.lpb_blocktri_solve(B, K, nb, self.nbd, Lp, Cp, sL, sC, C.c_void_p(self._bnd32.data_ptr()), C.c_void_p(rb.data_ptr()),
                                           C.c_void_p(out.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream))
         if rc == -1:
             self.fused_solve = False  # shape not supported: library solves from now on
@@ -409,6 +451,7 @@ class BlockTridiagKKT:
         return out
 
     def _solve(self, Ls, Cs, rb):
+        self.n_solve += 1
         fused = self._solve_fused(Ls, Cs, rb)
         if fused is not None:
             return fused

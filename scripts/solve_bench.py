@@ -61,7 +61,8 @@ def main():
                       "converged": ok, "seconds": dt, "iters_mean": float(r["iters"].double().mean().item()), "iters_max": int(r["iters"].max().item()),
                       "kkt_error_max": float(r["kkt_error"].max().item()), "objective_mean": float(r["obj"].mean().item()),
                       "n": ev.n, "m": ev.m, "nnz_jac": ev.nnz_jac, "nnz_h": ev.nnz_h, "transcription_kernel_launches": g.kernel_launches - l0,
-                      "tol": args.tol, "chunk": args.chunk, "kkt": ipm.kkt_kind, "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9}))
+                      "tol": args.tol, "chunk": args.chunk, "kkt": ipm.kkt_kind, "kkt_factorisations": getattr(ipm.kkt, "n_factor", None),
+                      "kkt_solves": getattr(ipm.kkt, "n_solve", None), "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9}))
 
 
 if __name__ == "__main__":

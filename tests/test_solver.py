@@ -102,7 +102,7 @@ def test_gpu_solves_match_cpu_reference_objectives(problem, kw, nb, spread):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("B,K,nb,nbd", [(3, 1, 7, 1), (5, 4, 33, 5), (64, 8, 140, 22), (2, 3, 160, 160)])
+@pytest.mark.parametrize("B,K,nb,nbd", [(3, 1, 7, 1), (5, 4, 33, 5), (64, 8, 140, 22), (2, 3, 96, 96), (3, 2, 200, 9)])
 def test_fused_block_tridiagonal_solve_matches_library(B, K, nb, nbd):
     """lpb_blocktri_solve (one launch per batched block-tridiagonal solve) against the same substitution through
     torch.linalg triangular solves, on random SPD block-tridiagonal systems; and against the assembled dense system."""
@@ -142,9 +142,41 @@ def test_fused_block_tridiagonal_solve_matches_library(B, K, nb, nbd):
     out = torch.empty_like(rd)
     Lp = (C.c_void_p * K)(*[L.data_ptr() for L in Ld])
     Cp = (C.c_void_p * max(K - 1, 1))(*([c.data_ptr() for c in Cd] or [0]))
-    rc = lib.lpb_blocktri_solve(B, K, nb, nbd, Lp, Cp, C.c_void_p(bnd32.data_ptr()), C.c_void_p(rd.data_ptr()), C.c_void_p(out.data_ptr()),
-                                C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    rc = lib.lpb_blocktri_solve(B, K, nb, nbd, Lp, Cp, nb * nb, nbd * nb, C.c_void_p(bnd32.data_ptr()), C.c_void_p(rd.data_ptr()),
+                                C.c_void_p(out.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream))
     assert rc == 0
     torch.cuda.synchronize()
     err = float(((out.cpu() - xref).abs().max() / xref.abs().max()).item())
     assert err <= 1e-11, err
+    # the fused factorisation: same factors as the library recursion, and factor + solve reproduce the dense solution
+    Dd, Ed = D.to(dev).contiguous(), E.to(dev).contiguous()
+    Lall, Call = torch.empty_like(Dd), torch.empty_like(Ed)
+    info = torch.full((B,), -7, dtype=torch.int32, device=dev)
+    rc = lib.lpb_blocktri_factor(B, K, nb, nbd, C.c_void_p(Dd.data_ptr()), C.c_void_p(Ed.data_ptr()), C.c_void_p(bnd32.data_ptr()),
+                                 C.c_void_p(Lall.data_ptr()), C.c_void_p(Call.data_ptr()), C.c_void_p(info.data_ptr()),
+                                 C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert int(info.abs().sum().item()) == 0
+    for i in range(K):
+        assert float((torch.tril(Lall[:, i]).cpu() - Ls[i]).abs().max().item()) <= 1e-10 * float(Ls[i].abs().max().item())
+        if i + 1 < K:
+            assert float((Call[:, i].cpu() - Cs[i]).abs().max().item()) <= 1e-10 * max(1.0, float(Cs[i].abs().max().item()))
+    Lp2 = (C.c_void_p * K)(*[Lall[:, i].data_ptr() for i in range(K)])
+    Cp2 = (C.c_void_p * max(K - 1, 1))(*([Call[:, i].data_ptr() for i in range(K - 1)] or [0]))
+    out2 = torch.empty_like(rd)
+    rc = lib.lpb_blocktri_solve(B, K, nb, nbd, Lp2, Cp2, K * nb * nb, max(K - 1, 1) * nbd * nb, C.c_void_p(bnd32.data_ptr()), C.c_void_p(rd.data_ptr()),
+                                C.c_void_p(out2.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert float(((out2.cpu() - xref).abs().max() / xref.abs().max()).item()) <= 1e-11
+    # an indefinite instance is reported (inertia test), the others are unaffected, everything stays finite
+    if B >= 2:
+        Dbad = Dd.clone()
+        Dbad[1, K - 1] -= 3.0 * nb * torch.eye(nb, dtype=torch.float64, device=dev)
+        rc = lib.lpb_blocktri_factor(B, K, nb, nbd, C.c_void_p(Dbad.data_ptr()), C.c_void_p(Ed.data_ptr()), C.c_void_p(bnd32.data_ptr()),
+                                     C.c_void_p(Lall.data_ptr()), C.c_void_p(Call.data_ptr()), C.c_void_p(info.data_ptr()),
+                                     C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        inf = info.cpu()
+        assert rc == 0 and int(inf[1]) > (K - 1) * nb and int(inf[0]) == 0 and bool(torch.isfinite(torch.tril(Lall[1])).all())
