@@ -468,8 +468,9 @@ def main():
                   "iters_mean": float(it_sum.item()) / (ns_ * world), "tol": 1e-6, "nnz_h_probed": ev.nnz_h,
                   "clocks_rank0": {k: solve_clocks.get(k) for k in ("sm_mhz", "sm_max_mhz", "reasons")},
                   "seconds_per_rank": [round(v, 3) for v in per_rank[:, 0].tolist()], "iters_max_per_rank": [int(v) for v in per_rank[:, 1].tolist()],
-                  "solver": "lockstep primal-dual interior point, exact FD Hessian, KKT step: %s (torch.linalg batched Cholesky / "
-                            "triangular solves); NLP callbacks = device-resident transcription kernels" % ipm.kkt_kind}
+                  "solver": "lockstep primal-dual interior point, exact FD Hessian, KKT step: %s; block solves = lpb_blocktri_solve "
+                            "(one launch per solve), factorisation = %s; NLP callbacks = device-resident transcription kernels"
+                            % (ipm.kkt_kind, "lpb_blocktri_factor" if getattr(ipm.kkt, "fused_factor", False) else "cuSOLVER batched Cholesky + cuBLAS")}
         del g2, ev, ipm, res
 
     if rank == 0:
