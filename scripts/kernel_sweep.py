@@ -26,7 +26,7 @@ def main():
     ap.add_argument("--unroll", type=int, nargs="*", default=[-1])
     ap.add_argument("--split", type=int, nargs="*", default=[0])
     ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--stage", type=int, nargs="*", default=[1], help="shared-memory staged write-out of the Jacobian values (where it applies)")
+    ap.add_argument("--stage", type=int, nargs="*", default=[0], help="shared-memory staged write-out of the Jacobian values (where it applies)")
     ap.add_argument("--rotate", type=int, nargs="*", default=[1], help="thread -> node rotation of the Jacobian kernel (aligned stores)")
     ap.add_argument("--hessian", action="store_true")
     ap.add_argument("--fg", action="store_true", help="also time eval_f and eval_grad_f")
