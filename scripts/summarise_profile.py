@@ -39,8 +39,9 @@ def launches(tag, path):
     tot = sum(sum(v) for v in d.values())
     with open(os.path.join(ROOT, "profiles", tag + "_launches_summary.txt"), "w") as f:
         f.write("# ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised: compare shares)\n")
-        f.write("# grouped by (kernel, grid): the timed step of bench.py launches k_cons_jac + k_endpoint over the whole batch\n")
-        f.write("# (grid x = 2048 / y = 4096); the 8x smaller grids and k_return_head belong to the chunked host-pointer (e2e) call\n")
+        f.write("# grouped by (kernel, grid): the timed step of bench.py is ONE k_cons_jac launch over the whole batch (grid x = 2048;\n")
+        f.write("# the quadrotor has no events or linkages, so no k_endpoint); the 8x smaller grids and k_return_head belong to the\n")
+        f.write("# chunked host-pointer (e2e) call\n")
         f.write("%8s %12s %12s %7s  %-18s kernel\n" % ("launches", "avg_ns", "total_ns", "share", "grid"))
         for (k, g), v in d.items():
             f.write("%8d %12.0f %12.0f %6.1f%%  %-18s %s\n" % (len(v), sum(v) / len(v), sum(v), 100 * sum(v) / tot, g, k[:150]))
