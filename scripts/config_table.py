@@ -111,6 +111,13 @@ def main():
             print("%-26s %9s %9s %10s | %-8s %10.4f %10.3f %10.3f %10s" % (name if first else "", n if first else "", m if first else "", nnz if first else "",
                                                                     cb, d, h, hp, ("%.2f%s" % (r, "*" if port else "")) if r is not None else "-"), flush=True)
             first = False
+        if nb == 1:
+            # per-mesh and per-solve steps around the callbacks (host wall clock, one problem): index maps + tables
+            # rebuilt on the GPU, NLP -> optimal-control conversion, mesh-error estimate
+            ms_refresh = wall_ms(g.refresh, 3)
+            ms_n2o = wall_ms(lambda: g.nlp2op(X[0], lam), 3)
+            ms_err = wall_ms(lambda: g.mesh_error(X[0]), 3)
+            print("%-26s %9s %9s %10s | refresh (tables + index maps on the GPU) %.3f ms, nlp2op %.3f ms, mesh_error %.3f ms" % ("", "", "", "", ms_refresh, ms_n2o, ms_err), flush=True)
         del g
 
 
