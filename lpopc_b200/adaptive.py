@@ -5,7 +5,8 @@ Mirrors the mesh loop of the reference's LpopcAlgorithm::SolveOptimalControlProb
 GetSizes; GetBounds; GetGuess; SolveNlp; Nlp2OpControl; }`).  Every new grid means new n, m, nnz and
 new index maps: `lpb_set_mesh` + `lpb_refresh` rebuild them on the GPU (north_star item 3); the error
 estimate between two solves runs on the GPU as well (`lpb_mesh_error`).  The outer
-NLP solver is lpopc_b200.solver.BatchedIPM (batch of one), standing in for IPOPT.
+NLP solver is lpopc_b200.solver.BatchedIPM (batch of one, GPU-resident) or a host solver on the TNLP callbacks
+(`slsqp_host_solver`), either standing in for IPOPT.
 
 Guess transfer between grids (N3, host side like the reference): the previous solution becomes the
 guess (Nlp2OPConverter.cpp:160-193) and is interpolated onto the new LGR nodes with a natural cubic
@@ -34,26 +35,63 @@ def transfer_guess(op, x, old_points, new_points):
     return np.concatenate(out)
 
 
+def slsqp_host_solver(ftol=1e-10, maxiter=600):
+    """A HOST outer NLP solver on the TNLP surface (bounds, f, grad f, g, Jacobian triplets): SciPy's SLSQP standing in
+    for IPOPT, which is not in this image (north_star keeps IPOPT and its linear solver on the host).  Dense
+    quasi-Newton SQP: meant for single problems of a few hundred variables (the reference's shipped examples).
+    Returns solve(nlp, x0) -> (x, objective, status, iterations) for solve_adaptive(host_solver=...)."""
+    import scipy.sparse as sp
+    from scipy.optimize import minimize
+
+    def solve(nlp, x0):
+        n, m = nlp.get_nlp_info()[:2]
+        jI, jJ = nlp.eval_jac_g(values=False)
+        xl, xu, gl, gu = nlp.get_bounds_info()
+        eq = gl == gu
+        lo_f, hi_f = (~eq) & (gl > -1e19), (~eq) & (gu < 1e19)
+        jac = lambda x: sp.coo_matrix((nlp.eval_jac_g(x), (jI, jJ)), shape=(m, n)).toarray()  # duplicates sum, as in IPOPT
+        cons = [dict(type="eq", fun=lambda x: nlp.eval_g(x)[eq] - gl[eq], jac=lambda x: jac(x)[eq])]
+        if lo_f.any():
+            cons.append(dict(type="ineq", fun=lambda x: nlp.eval_g(x)[lo_f] - gl[lo_f], jac=lambda x: jac(x)[lo_f]))
+        if hi_f.any():
+            cons.append(dict(type="ineq", fun=lambda x: gu[hi_f] - nlp.eval_g(x)[hi_f], jac=lambda x: -jac(x)[hi_f]))
+        bnds = [(None if lo < -1e19 else lo, None if hi > 1e19 else hi) for lo, hi in zip(xl, xu)]
+        r = minimize(nlp.eval_f, x0, jac=nlp.eval_grad_f, method="SLSQP", constraints=cons, bounds=bnds, options=dict(ftol=ftol, maxiter=maxiter))
+        g = nlp.eval_g(r.x)
+        viol = max(float(np.max(np.maximum(gl - g, 0))), float(np.max(np.maximum(g - gu, 0))))
+        return r.x, float(r.fun), 0 if viol <= 1e-6 else 1, int(r.nit)
+
+    return solve
+
+
 def solve_adaptive(op, make_nlp, make_evaluator, solver_cls, mesh_tol=1e-6, nmax=16, nmin=4, max_grids=10, ipm_tol=1e-6,
-                   max_iter=200, verbose=False):
+                   max_iter=200, verbose=False, host_solver=None):
     """Runs the mesh loop on `op` (its phases' meshes are updated in place).
 
     make_nlp(op) -> object with lgr_points(), initial_guess(), set_mesh(), refresh(), probe_dependencies(),
     refine_mesh_ph() (lpopc_b200.nlp.TranscribedNLP on the GPU); make_evaluator(nlp) -> evaluator for
-    solver_cls (lpopc_b200.solver.CudaEvaluator / BatchedIPM).  Returns (x, history)."""
+    solver_cls (lpopc_b200.solver.CudaEvaluator / BatchedIPM).  host_solver(nlp, x) -> (x, obj, status, iters), if
+    given, replaces the GPU-resident solver with a host outer loop on the TNLP callbacks (the reference's own
+    arrangement: IPOPT on the host, `slsqp_host_solver()` here).  Returns (x, history)."""
     nlp = make_nlp(op)
     x = nlp.initial_guess()
     nlp.probe_dependencies(x)  # once per problem, like LpopcAlgorithm::GetDependecies
     history = []
     for grid in range(1, max_grids + 1):
-        ev = make_evaluator(nlp)
-        res = solver_cls(ev, tol=ipm_tol, max_iter=max_iter).solve(x[None, :])
-        x = res["x"][0].cpu().numpy()
+        if host_solver is not None:
+            x, obj, status, iters = host_solver(nlp, x)
+            n_, m_, nnzj_, nnzh_ = nlp.get_nlp_info()
+        else:
+            ev = make_evaluator(nlp)
+            res = solver_cls(ev, tol=ipm_tol, max_iter=max_iter).solve(x[None, :])
+            x = res["x"][0].cpu().numpy()
+            obj, status, iters = float(res["obj"][0]), int(res["status"][0]), int(res["iters"][0])
+            n_, m_, nnzj_, nnzh_ = ev.n, ev.m, ev.nnz_jac, ev.nnz_h
         done, meshes = nlp.refine_mesh_ph(x, tol=mesh_tol, nmax=nmax, nmin=nmin)
         _, imax = nlp.mesh_error(x)
-        rec = {"grid": grid, "n": ev.n, "m": ev.m, "nnz_jac": ev.nnz_jac, "nnz_h": ev.nnz_h,
+        rec = {"grid": grid, "n": n_, "m": m_, "nnz_jac": nnzj_, "nnz_h": nnzh_,
                "nodes": [int(np.sum(p.nodesperinterval)) for p in op.phases], "intervals": [len(p.nodesperinterval) for p in op.phases],
-               "objective": float(res["obj"][0]), "status": int(res["status"][0]), "iters": int(res["iters"][0]),
+               "objective": obj, "status": status, "iters": iters,
                "max_rel_error": float(max(v.max() for v in imax)), "mesh_satisfied": bool(done)}
         history.append(rec)
         if verbose:

@@ -38,3 +38,20 @@ def test_adaptive_loop_hypersensitive_on_gpu():
     assert hist[-1]["max_rel_error"] <= 16e-5  # within the factor N_k <= Nmax of the tolerance that the truncation leaves
     assert abs(hist[-1]["objective"] - 1.33077) <= 2e-3  # value the refined meshes converge to
     assert x.size == hist[-1]["n"]
+
+
+@pytest.mark.gpu
+def test_adaptive_loop_brachistochrone_with_host_outer_solver_on_gpu():
+    """Single phase, free final time, through the whole mesh loop with a HOST outer solver on the CUDA TNLP
+    callbacks -- the reference's own arrangement (IPOPT on the host; SciPy SLSQP here): solve -> GPU mesh-error
+    estimate -> ph refinement -> GPU re-transcription (new index maps) -> spline warm start, until the mesh
+    satisfies the tolerance."""
+    from lpopc_b200 import nlp
+    op = examples.brachistochrone(intervals=2, nodes=4)
+    x, hist = adaptive.solve_adaptive(op, nlp.TranscribedNLP, None, None, mesh_tol=1e-7, max_grids=8,
+                                      host_solver=adaptive.slsqp_host_solver(ftol=1e-12))
+    assert len(hist) >= 2 and all(h["status"] == 0 for h in hist)
+    assert hist[-1]["mesh_satisfied"] and hist[-1]["max_rel_error"] <= 1e-7 < hist[0]["max_rel_error"]
+    assert hist[-1]["n"] > hist[0]["n"] and x.size == hist[-1]["n"]
+    # the refined mesh reproduces the fine fixed-mesh optimum of the same functor (tests/test_host_outer_loop.py)
+    assert abs(hist[-1]["objective"] - 0.824338669) <= 1e-8
