@@ -230,9 +230,10 @@ class BlockTridiagKKT:
     def __init__(self, ipm, blk_free, gamma=1e6, refine=3, fused=True):
         self.ipm, self.gamma, self.refine = ipm, gamma, refine
         # lpb_blocktri_factor (one launch, factor in shared memory) beats the library recursion for small blocks
-        # (nb = 44: 1.8 vs 3.5 ms per 4096-instance factorisation) and loses for large ones (nb = 140: 56 vs 29 ms,
-        # scripts/dev/blocktri_probe.py): the column-by-column update is latency-bound at 5 warps per CTA
-        self.fused_factor = bool(fused)  # narrowed to nb <= 64 once the block size is known (below)
+        # (nb = 44: 1.8 vs 3.5 ms per 4096-instance factorisation) and for small batches of large blocks (nb = 140,
+        # 64 instances: 2.0 vs 2.9 ms -- the straggler tail), and loses for large batches of large blocks (nb = 140,
+        # 4096 instances: 38 vs 29 ms, scripts/dev/blocktri_probe.py); _factor picks per call
+        self.fused_factor = bool(fused)
         self.n_factor = self.n_solve = 0  # factorisations / block-tridiagonal solves so far
         self.fused_solve = None if fused else False  # None: not probed yet, True: lpb_blocktri_solve, False: library triangular solves
         ev, dev = ipm.ev, ipm.ev.device
@@ -247,7 +248,6 @@ class BlockTridiagKKT:
         pos[order] = torch.arange(nf, device=dev) - starts[blk_free[order]]
         nb = int(counts.max().item())
         self.nb = nb
-        self.fused_factor = self.fused_factor and nb <= 64
         self.fpos = blk_free * nb + pos                      # free variable -> slot in the padded [K*nb] layout
         # Jacobian rows: group = lowest block among the row's free columns
         colmap = torch.full((ipm.n,), -1, dtype=torch.int64, device=dev)
@@ -393,7 +393,7 @@ class BlockTridiagKKT:
         """Block-tridiagonal Cholesky with boundary-row off-diagonal blocks: L_i L_i^T = A_i - (C_i C_i^T on the
         boundary slots), C_i = E_i L_{i-1}^-T [nbd x nb].  Returns (list L_i, list C_i, info)."""
         self.n_factor += 1
-        fused = self._factor_fused(Dp, Ep) if self.fused_factor else None
+        fused = self._factor_fused(Dp, Ep) if self.fused_factor and (self.nb <= 64 or Dp.shape[0] <= 256) else None
         if fused is not None:
             return fused
         Ls, Cs = [], []
