@@ -543,11 +543,12 @@ def interval_blocks(op, n_total):
 class BatchedIPM:
     """Lockstep primal-dual interior-point method over a batch of instances of one NLP."""
 
-    def __init__(self, ev, tol=1e-6, max_iter=100, mu0=0.1, rho=1e3, verbose=False, var_blocks=None, kkt_gamma=1e6, kkt_refine=3, kkt_fused=True):
+    def __init__(self, ev, tol=1e-6, max_iter=100, mu0=0.1, rho=1e3, verbose=False, var_blocks=None, kkt_gamma=1e6, kkt_refine=3, kkt_fused=True, compact_at=0.5):
         """var_blocks: optional block id (mesh interval) per NLP variable (`interval_blocks(op, n)`): selects the
         block-tridiagonal KKT step when the problem's coupling allows it, the dense condensed step otherwise."""
         self.var_blocks = var_blocks
         self.kkt_gamma, self.kkt_refine, self.kkt_fused = kkt_gamma, kkt_refine, kkt_fused
+        self.compact_at = compact_at  # resume on the unconverged instances once fewer than this fraction is still active
         self.kkt_kind = "dense"
         _, _, gl, gu = ev.bounds()
         self.user_ev = ev
@@ -744,7 +745,7 @@ class BatchedIPM:
             if bool(done.all()):
                 break
             n_act = int((~done).sum())
-            if B >= 16 and 2 * n_act < B:  # resume on the unconverged instances only
+            if B >= 16 and n_act < self.compact_at * B:  # resume on the unconverged instances only
                 suspended = {"X": X, "lam": lam, "zL": zL, "zU": zU, "mu": mu, "nu": nu, "dw_last": dw_last, "iters": iters,
                              "active": ~done, "it": it}
                 break

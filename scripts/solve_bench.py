@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--probe", type=int, default=1, help="run the NaN dependency probe first (sparser Hessian pattern), like the reference")
     ap.add_argument("--verbose", action="store_true")
     ap.add_argument("--fused", type=int, default=1, help="1: lpb_blocktri_solve (one launch per block-tridiagonal solve), 0: library triangular solves")
+    ap.add_argument("--compact-at", type=float, default=0.5, help="compact the batch once fewer than this fraction of it is unconverged")
     ap.add_argument("--refine", type=int, default=3, help="iterative-refinement steps of the block-tridiagonal KKT step")
     ap.add_argument("--gamma", type=float, default=1e6, help="dual regularisation 1/delta of the block-tridiagonal KKT step")
     ap.add_argument("--dense", action="store_true", help="dense condensed KKT step instead of the block-tridiagonal one")
@@ -49,7 +50,7 @@ def main():
     XL, XU = batch.mpc_bounds(xl, xu, op, x0s)
     ipm = solver.BatchedIPM(ev, tol=args.tol, max_iter=150, verbose=args.verbose,
                             var_blocks=None if args.dense else solver.interval_blocks(op, ev.n),
-                            kkt_gamma=args.gamma, kkt_refine=args.refine, kkt_fused=bool(args.fused))
+                            kkt_gamma=args.gamma, kkt_refine=args.refine, kkt_fused=bool(args.fused), compact_at=args.compact_at)
     ipm.solve(X0[:8], XL[:8], XU[:8])  # warm-up (cuSOLVER handles, kernels)
     torch.cuda.synchronize()
     l0, t0 = g.kernel_launches, time.perf_counter()
