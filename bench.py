@@ -470,7 +470,8 @@ def main():
                   "seconds_per_rank": [round(v, 3) for v in per_rank[:, 0].tolist()], "iters_max_per_rank": [int(v) for v in per_rank[:, 1].tolist()],
                   "solver": "lockstep primal-dual interior point, exact FD Hessian, KKT step: %s; block solves = lpb_blocktri_solve "
                             "(one launch per solve), factorisation = %s; NLP callbacks = device-resident transcription kernels"
-                            % (ipm.kkt_kind, "lpb_blocktri_factor" if getattr(ipm.kkt, "fused_factor", False) else "cuSOLVER batched Cholesky + cuBLAS")}
+                            % (ipm.kkt_kind, "lpb_blocktri_factor for blocks <= 64 or <= 256 active instances, cuSOLVER batched Cholesky + cuBLAS otherwise"
+                               if getattr(ipm.kkt, "fused_factor", False) else "cuSOLVER batched Cholesky + cuBLAS")}
         del g2, ev, ipm, res
 
     if rank == 0:
