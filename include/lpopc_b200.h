@@ -181,6 +181,9 @@ int lpb_structure_dev(lpb_handle* h, const int** d_jac_iRow, const int** d_jac_j
                       const int** d_h_iRow, const int** d_h_jCol);
 
 /* ---- linear algebra of the batched outer solver (lpopc_b200/solver.py) ----
+ * Stands where the reference has IPOPT's sparse linear solver behind NLPSolver::SolveNlp (LpNLPSolver.cpp:13-54,
+ * IpoptApplication::OptimizeTNLP :45): for a BATCH of instances the KKT step is one structured factorisation per
+ * instance on the GPU instead of one host solve at a time.
  * Batched block-tridiagonal positive definite systems over the mesh intervals: B instances, K diagonal blocks of
  * nb x nb, off-diagonal coupling only through the nbd boundary slots bnd[] (ascending) of the next block.
  * lpb_blocktri_factor: Dp [B][K][nb][nb] (symmetric, lower triangle read), Ep [B][K-1][nbd][nb] ->

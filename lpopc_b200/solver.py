@@ -563,6 +563,9 @@ class BatchedIPM:
         fixed = xl[0] == xu[0]
         if not bool(((xl == xu) == fixed.unsqueeze(0)).all()):
             raise ValueError("the set of fixed variables must be the same for every instance")
+        if getattr(self, "_setup_fixed", None) is not None and torch.equal(fixed, self._setup_fixed):
+            return  # same structure as the previous chunk / resumed sub-batch: index maps and KKT layout are reused
+        self._setup_fixed = fixed.clone()
         self.free = torch.nonzero(~fixed).squeeze(1)
         self.nf = int(self.free.numel())
         colmap = torch.full((self.n,), -1, dtype=torch.int64, device=dev)
