@@ -40,6 +40,28 @@ __global__ void __launch_bounds__(128) k_rotated(double* out, int nb, int N, siz
     for (int blk = 0; blk < NBLOCKS; ++blk) __stcs(vb + (unsigned)blk * (unsigned)N, v + blk);
 }
 
+// store flavours for the colour-major pattern: 0 = st.global.cs (what the kernels use), 1 = plain, 2 = .cg, 3 = .wt
+template <int MODE> __device__ __forceinline__ void st_mode(double* p, double v)
+{
+    if (MODE == 0) __stcs(p, v);
+    else if (MODE == 1) *p = v;
+    else if (MODE == 2) __stcg(p, v);
+    else __stwt(p, v);
+}
+template <int NROW, int NB, int MODE>
+__global__ void __launch_bounds__(128) k_colour_major_mode(double* out, int nb, int N, size_t pitch, double v)
+{
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)nb * N) return;
+    const int b = (int)(gid / N);
+    const int k = (int)(gid - (long long)b * N);
+    double* vb = out + (size_t)b * pitch + k;
+#pragma unroll 1
+    for (int cc = 0; cc < NB; ++cc)
+#pragma unroll
+        for (int i = 0; i < NROW; ++i) st_mode<MODE>(vb + (unsigned)(i * NB + cc) * (unsigned)N, v + cc);
+}
+
 // E/F: the kernel's real store ORDER: colour-major (for cc: for row i: block i*NB + cc), unrotated / rotated
 template <int NROW, int NB, bool ROT>
 __global__ void __launch_bounds__(128) k_colour_major(double* out, int nb, int N, size_t pitch, double v)
@@ -201,6 +223,15 @@ int main()
     }
     float pi = time_ms([&] { k_pair<12, 19><<<(nb * N / 2 + 127) / 128, 128>>>(out, nb, N, nnz, 1.0); }, 20);
     printf("I pairs, 16 B stores, colour-major %.4f ms  %.0f GB/s\n", pi, bytes / pi / 1e6);
+    {
+        float m0 = time_ms([&] { k_colour_major_mode<12, 19, 0><<<(nb * N + 127) / 128, 128>>>(out, nb, N, nnz, 1.0); }, 20);
+        float m1 = time_ms([&] { k_colour_major_mode<12, 19, 1><<<(nb * N + 127) / 128, 128>>>(out, nb, N, nnz, 1.0); }, 20);
+        float m2 = time_ms([&] { k_colour_major_mode<12, 19, 2><<<(nb * N + 127) / 128, 128>>>(out, nb, N, nnz, 1.0); }, 20);
+        float m3 = time_ms([&] { k_colour_major_mode<12, 19, 3><<<(nb * N + 127) / 128, 128>>>(out, nb, N, nnz, 1.0); }, 20);
+        printf("colour-major store flavours: .cs %.0f GB/s, plain %.0f GB/s, .cg %.0f GB/s, .wt %.0f GB/s\n", bytes / m0 / 1e6, bytes / m1 / 1e6, bytes / m2 / 1e6, bytes / m3 / 1e6);
+        float b64 = time_ms([&] { k_colour_major_mode<12, 19, 0><<<(nb * N + 63) / 64, 64>>>(out, nb, N, nnz, 1.0); }, 20);
+        printf("colour-major .cs with 64-thread CTAs: %.0f GB/s\n", bytes / b64 / 1e6);
+    }
     printf("bytes per launch %.1f MB\n", bytes / 1e6);
     printf("A contiguous        %.4f ms  %.0f GB/s\n", a, bytes / a / 1e6);
     printf("B kernel pattern    %.4f ms  %.0f GB/s\n", b, bytes / b / 1e6);
