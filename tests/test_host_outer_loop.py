@@ -15,8 +15,6 @@ import os
 
 import numpy as np
 import pytest
-import scipy.sparse as sp
-from scipy.optimize import minimize
 
 import golden_lib
 from lpopc_b200 import examples
@@ -28,27 +26,30 @@ CASES = [("bryson_denham", dict(intervals=4, nodes=4), 1e-10), ("brachistochrone
 OTOL = 1e-8
 
 
+class _AsNLP:
+    """Oracle-style callbacks (tests/oracle_lib.Oracle, golden_lib.CudaAdapter) behind the TranscribedNLP method names
+    that lpopc_b200.adaptive.slsqp_host_solver drives."""
+
+    def __init__(self, cb):
+        self.cb = cb
+
+    def get_nlp_info(self): return self.cb.nlp_info()
+    def get_bounds_info(self): return self.cb.bounds()
+    def eval_f(self, x): return self.cb.eval_f(x)
+    def eval_grad_f(self, x): return self.cb.eval_grad_f(x)
+    def eval_g(self, x): return self.cb.eval_g(x)
+    def eval_jac_g(self, x=None, values=True): return self.cb.eval_jac_g(x) if values else self.cb.jac_structure()
+
+
 def host_solve(cb, x0, ftol):
-    """SLSQP on the TNLP-shaped callbacks `cb` (nlp_info, bounds, eval_f, eval_grad_f, eval_g, jac triplets)."""
-    n, m = cb.nlp_info()[:2]
-    jI, jJ = cb.jac_structure()
+    """The product's host outer solver (SciPy SLSQP on the TNLP surface, lpopc_b200/adaptive.py) on callbacks `cb`:
+    (objective, max constraint violation, iterations)."""
+    from lpopc_b200 import adaptive
+    x, obj, _, nit = adaptive.slsqp_host_solver(ftol=ftol)(_AsNLP(cb), x0)
     xl, xu, gl, gu = cb.bounds()
-    eq = gl == gu
-    lo_f, hi_f = (~eq) & (gl > -1e19), (~eq) & (gu < 1e19)
-
-    def jac(x):  # duplicate triplets sum, as IPOPT does
-        return sp.coo_matrix((cb.eval_jac_g(x), (jI, jJ)), shape=(m, n)).toarray()
-
-    cons = [dict(type="eq", fun=lambda x: cb.eval_g(x)[eq] - gl[eq], jac=lambda x: jac(x)[eq])]
-    if lo_f.any():
-        cons.append(dict(type="ineq", fun=lambda x: cb.eval_g(x)[lo_f] - gl[lo_f], jac=lambda x: jac(x)[lo_f]))
-    if hi_f.any():
-        cons.append(dict(type="ineq", fun=lambda x: gu[hi_f] - cb.eval_g(x)[hi_f], jac=lambda x: -jac(x)[hi_f]))
-    bnds = [(None if lo < -1e19 else lo, None if hi > 1e19 else hi) for lo, hi in zip(xl, xu)]
-    r = minimize(cb.eval_f, x0, jac=cb.eval_grad_f, method="SLSQP", constraints=cons, bounds=bnds, options=dict(ftol=ftol, maxiter=600))
-    g = cb.eval_g(r.x)
+    g = cb.eval_g(x)
     viol = max(float(np.max(np.maximum(gl - g, 0))), float(np.max(np.maximum(g - gu, 0))))
-    return float(r.fun), viol, int(r.nit)
+    return obj, viol, nit
 
 
 def _start(op, o):
