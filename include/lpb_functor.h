@@ -54,4 +54,21 @@
 
 #include "lpb_detmath.h"
 
+/* Bit mask of variable indices in the order [states, controls, time], for the optional member
+ *     static constexpr unsigned long long HESS_DEP[NS + NPATH + 1];
+ * one mask per dae row, per path row, and one for the Lagrange integrand: the variables the row reads.  It is the
+ * compile-time counterpart of the reference's NaN dependency probe (LpDerivDependciesChecker.cpp:10-94) and lets
+ * the Hessian kernel generate a stencil only for the (row, variable pair) combinations that can be non-zero
+ * (lpb_hessian.cuh).  A superset is always safe; a missing bit is rejected by lpb_probe_dependencies, which
+ * compares the table with the probe's result.  Functor sets without the table use the generic pair loops. */
+#ifdef __cplusplus
+#include <initializer_list>
+constexpr unsigned long long lpb_vars(std::initializer_list<int> vars)
+{
+    unsigned long long m = 0;
+    for (int v : vars) m |= 1ull << v;
+    return m;
+}
+#endif
+
 #endif /* LPB_FUNCTOR_H */

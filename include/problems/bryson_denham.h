@@ -9,7 +9,8 @@ struct LpbBrysonDenham {
     static constexpr int NS = 3, NC = 1, NPATH = 0, NE_MAX = 5, NL_MAX = 0;
     static constexpr bool HAS_ANALYTIC = false;
     static constexpr bool UNROLL_COLOURS = true; /* compile-time colour unrolling of the FD Jacobian kernel */
-    static constexpr bool UNROLL_HESSIAN = UNROLL_COLOURS; /* pragma-unrolled pair loops of the Hessian kernel */
+    /* variables read per dae row and by the Lagrange integrand, order [x0..x2, u, t] (lpb_functor.h) */
+    static constexpr unsigned long long HESS_DEP[NS + NPATH + 1] = {lpb_vars({1}), lpb_vars({3}), lpb_vars({3}), lpb_vars({})};
     struct Consts { double unused; };
     static const char* name() { return "bryson_denham"; }
 

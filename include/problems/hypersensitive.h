@@ -10,7 +10,8 @@ struct LpbHypersensitive {
     static constexpr int NS = 1, NC = 1, NPATH = 0, NE_MAX = 0, NL_MAX = 0;
     static constexpr bool HAS_ANALYTIC = true;
     static constexpr bool UNROLL_COLOURS = true; /* compile-time colour unrolling of the FD Jacobian kernel */
-    static constexpr bool UNROLL_HESSIAN = UNROLL_COLOURS; /* pragma-unrolled pair loops of the Hessian kernel */
+    /* variables read per dae row and by the Lagrange integrand, order [x, u, t] (lpb_functor.h) */
+    static constexpr unsigned long long HESS_DEP[NS + NPATH + 1] = {lpb_vars({0, 1}), lpb_vars({0, 1})};
     struct Consts { double unused; };
     static const char* name() { return "hypersensitive"; }
 

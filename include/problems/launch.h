@@ -12,7 +12,11 @@ struct LpbLaunch {
     static constexpr int NS = 7, NC = 3, NPATH = 1, NE_MAX = 5, NL_MAX = 7;
     static constexpr bool HAS_ANALYTIC = false;
     static constexpr bool UNROLL_COLOURS = true; /* compile-time colour unrolling of the FD Jacobian kernel */
-    static constexpr bool UNROLL_HESSIAN = UNROLL_COLOURS; /* pragma-unrolled pair loops of the Hessian kernel */
+    /* variables read per dae row, per path row and by the Lagrange integrand, order [r(3), v(3), m, u(3), t] */
+    static constexpr unsigned long long HESS_DEP[NS + NPATH + 1] = {
+        lpb_vars({3}), lpb_vars({4}), lpb_vars({5}),
+        lpb_vars({0, 1, 2, 3, 4, 5, 6, 7}), lpb_vars({0, 1, 2, 3, 4, 5, 6, 8}), lpb_vars({0, 1, 2, 3, 4, 5, 6, 9}),
+        lpb_vars({}), lpb_vars({7, 8, 9}), lpb_vars({})};
     /* CONSTANTS of Launch.cpp:50-74,148-153 (omega = earthRotRate*scales.time) */
     struct Consts {
         double omega, mu, cd, sa, rho0, H, Re, g0;

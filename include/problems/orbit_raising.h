@@ -11,7 +11,10 @@ struct LpbOrbitRaising {
     static constexpr int NS = 5, NC = 2, NPATH = 1, NE_MAX = 2, NL_MAX = 0;
     static constexpr bool HAS_ANALYTIC = false;
     static constexpr bool UNROLL_COLOURS = true; /* compile-time colour unrolling of the FD Jacobian kernel */
-    static constexpr bool UNROLL_HESSIAN = UNROLL_COLOURS; /* pragma-unrolled pair loops of the Hessian kernel */
+    /* variables read per dae row, per path row and by the Lagrange integrand, order [r, theta, vr, vt, m, u0, u1, t] */
+    static constexpr unsigned long long HESS_DEP[NS + NPATH + 1] = {
+        lpb_vars({2}), lpb_vars({0, 3}), lpb_vars({0, 3, 4, 5}), lpb_vars({0, 2, 3, 4, 6}), lpb_vars({}),
+        lpb_vars({5, 6}), lpb_vars({})};
     struct Consts { double T, mu, mdot; };
     static const char* name() { return "orbit_raising"; }
 

@@ -12,7 +12,13 @@ struct LpbQuadrotor {
     static constexpr int NS = 12, NC = 4, NPATH = 0, NE_MAX = 0, NL_MAX = 0;
     static constexpr bool HAS_ANALYTIC = false;
     static constexpr bool UNROLL_COLOURS = true; /* compile-time colour unrolling of the FD Jacobian kernel */
-    static constexpr bool UNROLL_HESSIAN = UNROLL_COLOURS; /* pragma-unrolled pair loops of the Hessian kernel */
+    /* variables read per dae row and by the Lagrange integrand, order [x0..x11, u0..u3, t] (lpb_functor.h) */
+    static constexpr unsigned long long HESS_DEP[NS + NPATH + 1] = {
+        lpb_vars({3}), lpb_vars({4}), lpb_vars({5}),
+        lpb_vars({6, 7, 8, 12, 13, 14, 15}), lpb_vars({6, 7, 8, 12, 13, 14, 15}), lpb_vars({6, 7, 12, 13, 14, 15}),
+        lpb_vars({6, 7, 9, 10, 11}), lpb_vars({6, 10, 11}), lpb_vars({6, 7, 10, 11}),
+        lpb_vars({10, 11, 13, 15}), lpb_vars({9, 11, 12, 14}), lpb_vars({9, 10, 12, 13, 14, 15}),
+        lpb_vars({0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15})};
     struct Consts {
         double mass, g, Ixx, Iyy, Izz, arm, kM;
         double qp, qv, qa, qw, ru;

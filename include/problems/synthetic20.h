@@ -10,7 +10,7 @@ struct LpbSynthetic20 {
     static constexpr int NS = 20, NC = 6, NPATH = 0, NE_MAX = 0, NL_MAX = 0;
     static constexpr bool HAS_ANALYTIC = false;
     static constexpr bool UNROLL_COLOURS = false; /* compile-time colour unrolling of the FD Jacobian kernel */
-    static constexpr bool UNROLL_HESSIAN = false; /* 378 dense pair bodies: keep the run-time pair loops */
+    /* no HESS_DEP table: every row reads every state (378 dense pair bodies): the Hessian keeps the run-time pair loops */
     struct Consts { double A[NS * NS]; double B[NS * NC]; }; /* row-major */
     static const char* name() { return "synthetic20"; }
 

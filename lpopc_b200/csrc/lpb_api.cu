@@ -1395,6 +1395,19 @@ int lpb_probe_dependencies(lpb_handle* h, const double* x_guess, int* dep_out)
     std::vector<int> dep(per * h->ph.size());
     CK(cudaMemcpyAsync(dep.data(), h->d_dep.p, dep.size() * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    if (const unsigned long long* decl = h->vt->hess_dep) {
+        // the tiled Hessian kernel is generated from the functor set's declared masks: a dependency the probe
+        // sees and the table does not declare would silently drop stencil rows
+        for (size_t ip = 0; ip < h->ph.size(); ++ip)
+            for (int v = 0; v < ns + nc; ++v)
+                for (int r = 0; r < ns + np; ++r)
+                    if (dep[ip * per + (size_t)v * (ns + np) + r] && !((decl[r] >> v) & 1ull)) {
+                        char msg[160];
+                        std::snprintf(msg, sizeof msg, "functor set '%s': HESS_DEP does not declare that row %d reads variable %d (phase %d)",
+                                      h->vt->name, r, v, (int)ip + 1);
+                        throw ApiError(LPB_ERR_INVALID, msg);
+                    }
+    }
     for (size_t ip = 0; ip < h->ph.size(); ++ip) h->ph[ip].dep.assign(dep.begin() + ip * per, dep.begin() + (ip + 1) * per);
     if (dep_out) std::memcpy(dep_out, dep.data(), dep.size() * sizeof(int));
     refresh(h); // the Hessian pattern depends on the mask (LpHessian.cpp:2532-2536)
@@ -1428,6 +1441,7 @@ int lpb_set_option_int(lpb_handle* h, const char* name, int value)
         rebuild_sparse_plan(h);
     }
     else if (!std::strcmp(name, "unroll_colours")) h->opts.unroll_colours = value;
+    else if (!std::strcmp(name, "hess_variant")) h->opts.hess_variant = value;
     else if (!std::strcmp(name, "rotate_nodes")) h->opts.no_rotate = value ? 0 : 1;
     else if (!std::strcmp(name, "stage_values")) h->opts.stage_values = value;
     else if (!std::strcmp(name, "time_kernels")) h->time_kernels = value != 0;

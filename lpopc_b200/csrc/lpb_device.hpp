@@ -95,7 +95,9 @@ struct LaunchOpts {
                         // over PCIe on every call)
     int stage_values;   // Jacobian kernel: 1 = shared-memory staged write-out where it applies, 0 = per-thread scatter (option "stage_values")
     int no_rotate;      // 1: do not rotate the thread -> node map of the Jacobian kernel (A/B measurement)
-    int unroll_colours; // Jacobian kernel variant: -1 = functor default (P::UNROLL_COLOURS), 0 = colour loop, 1 = unrolled
+    int unroll_colours; // Jacobian kernel variant: -1 = functor default (P::UNROLL_COLOURS), 0 = colour loop, 1 = unrolled;
+                        // Hessian node kernel: 0 = generic pair loops, otherwise the tiled kernel where the functor set has HESS_DEP
+    int hess_variant;   // tuning builds (-DLPB_HESS_VARIANTS): (tile size, CTAs/SM) instantiation of the tiled Hessian kernel
     // optional CUDA events recorded on the launch stream right before / after the dominant
     // node kernel (bench.py's live roofline measurement); null = no timing
     cudaEvent_t ev_begin, ev_end;
@@ -124,6 +126,8 @@ struct FunctorVTable {
     // NLP solution -> optimal-control solution (lpb_convert.cuh); out == nullptr: layout query only
     int (*nlp2op)(const ProblemDev& pd, const void* consts, cudaStream_t st, const double* x, const double* lambda,
                   double* out, double* scratch, long long* phase_offsets);
+    // declared dependency masks of the functor set (P::HESS_DEP, NS + NPATH + 1 entries) or null
+    const unsigned long long* hess_dep;
 };
 
 const FunctorVTable* const* functor_registry(int* count);

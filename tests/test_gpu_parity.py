@@ -284,3 +284,39 @@ def test_staged_jacobian_kernel_is_bit_identical(nlp_mod, name, nb):
     assert np.array_equal(g_s.view(np.int64), g_p.view(np.int64))
     assert rel_err(v_s[3], o.eval_jac_g(X[3])) <= RTOL
     assert rel_err(g_s[3], o.eval_g(X[3])) <= RTOL
+
+
+TILED_CASES = ["hypersensitive", "hypersensitive_analytic", "bryson_denham", "bryson_denham/ragged", "launch", "launch/ragged",
+               "orbit_raising", "brachistochrone", "quadrotor", "quadrotor/u8x8", "cartpole"]
+
+
+@pytest.mark.parametrize("probe", [False, True])
+@pytest.mark.parametrize("name", TILED_CASES)
+def test_tiled_hessian_kernel_is_bit_identical(nlp_mod, name, probe):
+    """k_hess_tiled (compile-time pair bodies generated from the functor set's HESS_DEP table: stencils only on rows
+    that read both variables, branch-free quotients) against k_hess_nodes (run-time pair loops over every row, IEEE
+    quotients): every Hessian value bit for bit, on the dense pattern and on the pattern the NaN probe leaves, at a
+    generic point and at a point where many function values are tiny next to their increments (the rounding terms of
+    rows that read only one variable of a pair are then non-zero)."""
+    op = cases.build(name)
+    o = Oracle(op)
+    g = nlp_mod.TranscribedNLP(op)
+    guess, x, sigma, lam = cases.inputs(op, o, 41)
+    if probe:
+        g.probe_dependencies(guess)
+    rng = np.random.Generator(np.random.PCG64(42))
+    x_small = x.copy()
+    # states and controls within 1e-7 of zero (times untouched): f is tiny where it vanishes at the origin
+    off = 0
+    for ph in op.phases:
+        N = int(np.sum(ph.nodesperinterval))
+        nvar = ph.statenum * (N + 1) + ph.controlnum * N
+        x_small[off:off + nvar] = 1e-7 * rng.uniform(-1, 1, nvar)
+        off += nvar + 2 + ph.parameternum
+    for xx in (x, x_small):
+        g.set_option("unroll_colours", -1)
+        h_t = g.eval_h(xx, sigma, lam)
+        g.set_option("unroll_colours", 0)  # generic pair loops
+        h_g = g.eval_h(xx, sigma, lam)
+        assert np.array_equal(h_t.view(np.int64), h_g.view(np.int64)), np.flatnonzero(h_t.view(np.int64) != h_g.view(np.int64))[:10]
+    g.close()
