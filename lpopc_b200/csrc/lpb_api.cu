@@ -332,6 +332,8 @@ struct PhaseHost {
     PhaseTables tab;
     std::vector<int> dep; // (ns+np) x (ns+nc), column-major, 0/1
     std::vector<int> pair_a, pair_b, hblk;
+    std::vector<HessRow> hrow;
+    DevBuf<HessRow> d_hrow;
     DevBuf<double> d_tau, d_w, d_ddiag, d_dblocks, d_doff_vals;
     DevBuf<int> d_node_interval, d_int_row0, d_int_n, d_doff_a, d_doff_b, d_hblk, d_pair_a, d_pair_b, d_counts;
     DevBuf<long long> d_int_d0;
@@ -511,8 +513,9 @@ static void refresh(lpb_handle* h)
         p.d_doff_a.reserve((size_t)ndoff + 1); p.d_doff_b.reserve((size_t)ndoff + 1); p.d_doff_vals.reserve((size_t)ndoff + 1);
         run_compaction(h, p, 0, p.d_doff_a.p, p.d_doff_b.p, p.d_doff_vals.p, false);
         if (p.dep.empty()) p.dep.assign((size_t)(ns + np) * (ns + nc), 1); // probe not run: dense mask
-        build_hess_blocks(ns, nc, np, p.dep, p.pair_a, p.pair_b, p.hblk);
+        build_hess_blocks(ns, nc, np, p.dep, p.pair_a, p.pair_b, p.hblk, &p.hrow);
         p.d_hblk.upload(p.hblk, h->stream);
+        p.d_hrow.upload(p.hrow, h->stream);
         p.d_pair_a.upload(p.pair_a, h->stream);
         p.d_pair_b.upload(p.pair_b, h->stream);
         PhaseShape& s = L.ph[ip];
@@ -540,7 +543,7 @@ static void refresh(lpb_handle* h)
         d.nl0 = L.nl0[ip]; d.ev0 = L.ev0[ip]; d.c0 = L.c0[ip]; d.hI0 = L.hI0[ip]; d.hE0 = L.hE0[ip];
         d.tau = p.d_tau.p; d.w = p.d_w.p; d.ddiag = p.d_ddiag.p; d.node_interval = p.d_node_interval.p;
         d.int_row0 = p.d_int_row0.p; d.int_n = p.d_int_n.p; d.int_d0 = p.d_int_d0.p; d.dblocks = p.d_dblocks.p;
-        d.doff_vals = p.d_doff_vals.p; d.hblk = p.d_hblk.p;
+        d.doff_vals = p.d_doff_vals.p; d.hblk = p.d_hblk.p; d.hrow = p.d_hrow.p;
     }
     for (int l = 0; l < Lp; ++l) {
         LinkDev& d = pd.lk[l];

@@ -42,6 +42,7 @@ struct PhaseDev {
     const double* dblocks;
     const double* doff_vals;  // [ndoff]
     const int* hblk;          // [(ns+nc)^2] block index of (row var, col var) in the Hessian I-part, -1 if absent
+    const HessRow* hrow;      // [ns+nc] the same per row as (presence mask, first block): one load per row (ns+nc <= 64)
 };
 
 struct LinkDev {

@@ -115,12 +115,14 @@ __device__ __forceinline__ void hess_store_pair(const PhaseDev& ph, const HessNo
 {
     typedef Dim<P> D;
     constexpr int NV = D::NS + D::NC;
-    const int N = nd.N, k = nd.k;
+    // 32-bit value offsets: an instance fits IPOPT's 32-bit Index (checked in build_layout)
+    const unsigned uN = (unsigned)nd.N;
+    double* __restrict__ vk = nd.vI + nd.k;
     if (!a_is_time) {
-        st_stream(nd.vI + (size_t)blk * N + k, core);
+        st_stream(vk + (unsigned)blk * uN, core);
     } else if (!b_is_time) {
-        st_stream(nd.vI + (size_t)(ph.nblkH + b) * N + k, 0.5 * A + nd.talpha * core);
-        st_stream(nd.vI + (size_t)(ph.nblkH + NV) * N + 1 + (size_t)b * N + k, -0.5 * A + nd.tbeta * core);
+        st_stream(vk + (unsigned)(ph.nblkH + b) * uN, 0.5 * A + nd.talpha * core);
+        st_stream(vk + ((unsigned)(ph.nblkH + NV + b) * uN + 1u), -0.5 * A + nd.tbeta * core);
     } else {
         // per-node terms of the three time-time scalars
         scr[gid] = nd.talpha * (A + nd.talpha * core);
@@ -360,15 +362,12 @@ __device__ __forceinline__ bool hess_tile(const ProblemDev& pd, const typename P
             La = P::lagrange(C, p + 1, ta, xa, ua);
         }
         constexpr int B1 = B1x < a + 1 ? B1x : a + 1;
+        HessRow hr{~0ull, 0, 0};
+        if constexpr (a < T) hr = ph.hrow[a]; // one load per row: which pairs (a, b) the pattern holds, and where
         static_for<B0, B1>([&](auto bc) {
             constexpr int b = decltype(bc)::value;
-            int blk = 0;
-            bool present = true;
-            if constexpr (a < T) {
-                blk = ph.hblk[a * NV + b];
-                present = blk >= 0; // pair absent from the pattern (dependency mask)
-            }
-            if (present) {
+            if ((hr.mask >> b) & 1ull) { // else: pair absent from the pattern (dependency mask)
+                const int blk = hr.blk0 + __popcll(hr.mask & ((1ull << b) - 1ull));
                 const double hb = hbs[b - B0];
                 const double* fb = fbs[b - B0];
                 const double* cb = cbs[b - B0];
@@ -677,13 +676,10 @@ int launch_hessian(const ProblemDev& pd, const void* consts, cudaStream_t st, co
             constexpr int G0 = hess_tile_size<P>::value, M0 = hess_min_ctas<P>::value;
 #ifdef LPB_HESS_VARIANTS
             switch (o.hess_variant) {
-            case 1: launch_hess_tiled<P, (D::NCOL < 4 ? D::NCOL : 4), 3>(pd, C, st, gx, nbatch, x, sigma, lambda, vals, scratch); break;
-            case 2: launch_hess_tiled<P, (D::NCOL < 4 ? D::NCOL : 4), 4>(pd, C, st, gx, nbatch, x, sigma, lambda, vals, scratch); break;
-            case 3: launch_hess_tiled<P, (D::NCOL < 6 ? D::NCOL : 6), 2>(pd, C, st, gx, nbatch, x, sigma, lambda, vals, scratch); break;
-            case 4: launch_hess_tiled<P, (D::NCOL < 6 ? D::NCOL : 6), 4>(pd, C, st, gx, nbatch, x, sigma, lambda, vals, scratch); break;
-            case 5: launch_hess_tiled<P, (D::NCOL < 9 ? D::NCOL : 9), 2>(pd, C, st, gx, nbatch, x, sigma, lambda, vals, scratch); break;
-            case 6: launch_hess_tiled<P, (D::NCOL < 9 ? D::NCOL : 9), 3>(pd, C, st, gx, nbatch, x, sigma, lambda, vals, scratch); break;
-            case 7: launch_hess_tiled<P, (D::NCOL < 3 ? D::NCOL : 3), 4>(pd, C, st, gx, nbatch, x, sigma, lambda, vals, scratch); break;
+            case 1: launch_hess_tiled<P, (D::NCOL < 6 ? D::NCOL : 6), 2>(pd, C, st, gx, nbatch, x, sigma, lambda, vals, scratch); break;
+            case 2: launch_hess_tiled<P, (D::NCOL < 6 ? D::NCOL : 6), 4>(pd, C, st, gx, nbatch, x, sigma, lambda, vals, scratch); break;
+            case 3: launch_hess_tiled<P, (D::NCOL < 5 ? D::NCOL : 5), 3>(pd, C, st, gx, nbatch, x, sigma, lambda, vals, scratch); break;
+            case 4: launch_hess_tiled<P, (D::NCOL < 9 ? D::NCOL : 9), 2>(pd, C, st, gx, nbatch, x, sigma, lambda, vals, scratch); break;
             default: launch_hess_tiled<P, G0, M0>(pd, C, st, gx, nbatch, x, sigma, lambda, vals, scratch); break;
             }
 #else
@@ -715,7 +711,7 @@ const unsigned long long* hess_dep_table()
     if constexpr (has_hess_dep<P>::value) {
         static_assert(sizeof(P::HESS_DEP) / sizeof(P::HESS_DEP[0]) == Dim<P>::NROW + 1,
                       "HESS_DEP needs one mask per dae row, per path row, and one for the Lagrange integrand");
-        static_assert(Dim<P>::NCOL <= 64, "HESS_DEP masks hold at most 64 variables");
+        static_assert(Dim<P>::NCOL <= 64 && Dim<P>::NROW < 64, "HESS_DEP masks hold at most 64 variables");
         static unsigned long long copy[Dim<P>::NROW + 1];
         for (int r = 0; r <= Dim<P>::NROW; ++r) copy[r] = P::HESS_DEP[r];
         return copy;

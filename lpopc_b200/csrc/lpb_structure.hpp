@@ -24,6 +24,9 @@ constexpr int kMaxPhases = 12;
 constexpr int kMaxLinks = 12;
 
 struct HessEntry { int a, b, da, db; }; // endpoint pair + the two perturbations of its denominator (quirk Q10)
+// row a of the xx/ux/uu block list of the Hessian I-part: bit b of mask = block (a, b) present; present blocks of a
+// row are consecutive, so block index(a, b) = blk0 + popcount(mask below bit b)
+struct HessRow { unsigned long long mask; int blk0; int pad; };
 
 // integer description of one phase, enough for every index formula
 struct PhaseShape {
@@ -375,7 +378,7 @@ inline void build_entry_tables(int ns, std::vector<HessEntry>& eent, std::vector
 // depH = dep' * dep with unit diagonal (LpHessian.cpp:2532-2536); lower-triangle block list in the
 // order of GetPhaseHessianSparsity :662-735.  dep is (ns+np) x (ns+nc) column-major 0/1.
 inline void build_hess_blocks(int ns, int nc, int np, const std::vector<int>& dep,
-                              std::vector<int>& pair_a, std::vector<int>& pair_b, std::vector<int>& hblk)
+                              std::vector<int>& pair_a, std::vector<int>& pair_b, std::vector<int>& hblk, std::vector<HessRow>* hrow = nullptr)
 {
     const int NV = ns + nc, NR = ns + np;
     std::vector<int> depH((size_t)NV * NV, 0);
@@ -400,6 +403,19 @@ inline void build_hess_blocks(int ns, int nc, int np, const std::vector<int>& de
             if (depH[(size_t)(ns + i) * NV + j]) add(ns + i, j);
         for (int j = 0; j <= i; ++j)
             if (depH[(size_t)(ns + i) * NV + ns + j]) add(ns + i, ns + j);
+    }
+    if (hrow) {
+        hrow->assign((size_t)NV, HessRow{0ull, 0, 0});
+        for (int a = 0; a < NV && a < 64; ++a) {
+            HessRow r{0ull, -1, 0};
+            for (int b = 0; b <= a; ++b)
+                if (hblk[(size_t)a * NV + b] >= 0) {
+                    if (r.blk0 < 0) r.blk0 = hblk[(size_t)a * NV + b];
+                    r.mask |= 1ull << b;
+                }
+            if (r.blk0 < 0) r.blk0 = 0;
+            (*hrow)[a] = r;
+        }
     }
 }
 
