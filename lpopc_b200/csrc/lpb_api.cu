@@ -1477,6 +1477,14 @@ int lpb_get_stat(lpb_handle* h, const char* name, long long* value)
     else if (!std::strcmp(name, "sparse_fixups")) *value = h->sparse_fixups;
     else if (!std::strcmp(name, "sparse_on_doubles")) *value = h->seg_mask_init ? (long long)h->on_doubles : -1;
     else if (!std::strcmp(name, "head_doubles")) *value = (long long)h->pd.lin_val0;
+    else if (!std::strncmp(name, "hess_I0.", 8) || !std::strncmp(name, "hess_E0.", 8) || !std::strncmp(name, "hess_L0.", 8)) {
+        // first Hessian value of the I-part / E-part of phase <p>, of the link part of pair <q> (parity reports by segment)
+        need_fresh(h);
+        const int i = std::atoi(name + 8);
+        const bool link = name[5] == 'L';
+        if (i < 0 || i >= (link ? h->pd.Lp : h->pd.P)) throw ApiError(LPB_ERR_INVALID, "segment index out of range");
+        *value = link ? h->pd.lk[i].h0 : (name[5] == 'I' ? h->pd.ph[i].hI0 : h->pd.ph[i].hE0);
+    }
     else if (!std::strcmp(name, "pinned_buffers")) {
         long long c = 0;
         for (auto& hb : h->host_bufs) c += hb.pinned ? 1 : 0;

@@ -66,6 +66,17 @@ def main():
             d["dep_info"] = np.array(r.nlp_info())
             d["dep_hI"], d["dep_hJ"] = r.h_structure()
             d["dep_hess"] = r.eval_h(x, sigma, lam)
+        base = name.split("/")[0]
+        if base in ("hypersensitive", "bryson_denham", "launch"):
+            # second opinion on include/problems/<base>.h: the same transcription with the reference's OWN example
+            # user functions (Armadillo expressions + libm; oracle/ref_examples.cpp)
+            op2 = cases.build(name)
+            op2.functor = "ref:" + base
+            r2 = RefOracle(op2)
+            assert r2.nlp_info() == r.nlp_info()
+            d["refex_f"], d["refex_grad"] = np.array(r2.eval_f(x)), r2.eval_grad_f(x)
+            d["refex_g"], d["refex_jac"] = r2.eval_g(x), r2.eval_jac_g(x)
+            d["refex_hess"] = r2.eval_h(x, sigma, lam)
         path = os.path.join(out, name.replace("/", "__") + ".npz")
         np.savez_compressed(path, **d)
         print("%-28s n=%-6d m=%-6d nnz_jac=%-7d nnz_h=%-7d %6.1f KB" % ((name,) + r.nlp_info() + (os.path.getsize(path) / 1024,)))

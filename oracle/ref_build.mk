@@ -20,12 +20,24 @@ REF_SRCS := SparseMatrix/LpSparseMatrix.cpp SparseMatrix/LpSparseArray.cpp \
             Core/LpGuessChecker.cpp Core/LpDerivDependciesChecker.cpp Core/LpFiniteDifferenceDerive.cpp \
             Core/LpNLPWrapper.cpp Core/LpHessian.cpp Core/LpSacleOCP.cpp Core/LpSolutionError.cpp Core/LpPhMeshRefineAlg.cpp Core/Nlp2OPConverter.cpp \
             Common/LpOption.cpp Common/LpOptionList.cpp Common/LpReporter.cpp Common/LpDebug.cpp Common/LpUtils.cpp
-OBJS := $(addprefix $(OUT)/,$(notdir $(REF_SRCS:.cpp=.o))) $(OUT)/ref_driver.o
+# the reference's example programs: their user-function classes are the second opinion on include/problems/*.h.
+# -Dmain=...: each example's main() becomes an unused internal function (it needs IPOPT to link)
+EXAMPLES ?= /root/reference/Lpopc/example
+EX_SRCS := hypersensitive/HyperSensitive.cpp bryson-denham/BrysonDenham.cpp launch/Launch.cpp
+EX_INC := -I$(EXAMPLES)/hypersensitive -I$(EXAMPLES)/bryson-denham -I$(EXAMPLES)/launch
+OBJS := $(addprefix $(OUT)/,$(notdir $(REF_SRCS:.cpp=.o))) $(addprefix $(OUT)/ex_,$(notdir $(EX_SRCS:.cpp=.o))) \
+        $(OUT)/ref_driver.o $(OUT)/ref_examples.o
 HDRS := oracle/ref_shim/armadillo $(wildcard include/*.h) $(wildcard include/problems/*.h)
-vpath %.cpp $(REF)/Core $(REF)/Common $(REF)/SparseMatrix oracle
+vpath %.cpp $(REF)/Core $(REF)/Common $(REF)/SparseMatrix oracle $(EXAMPLES)/hypersensitive $(EXAMPLES)/bryson-denham $(EXAMPLES)/launch
 
 $(OUT)/liblpopc_ref.so: $(OBJS)
 	$(CXX) -shared -pthread -o $@ $(OBJS)
+
+$(OUT)/ex_%.o: %.cpp $(HDRS) | $(OUT)
+	$(CXX) $(CXXFLAGS) -Dmain="static lpopc_example_main" -c $< -o $@
+
+$(OUT)/ref_examples.o: ref_examples.cpp $(HDRS) | $(OUT)
+	$(CXX) $(CXXFLAGS) $(EX_INC) -c $< -o $@
 
 $(OUT)/%.o: %.cpp $(HDRS) | $(OUT)
 	$(CXX) $(CXXFLAGS) -c $< -o $@

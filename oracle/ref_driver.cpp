@@ -206,8 +206,18 @@ shared_ptr<FunctionWrapper> make_adapter(const Ref& r)
     return shared_ptr<FunctionWrapper>(new RefAdapter<P>(r.consts.data(), (int)r.consts.size(), ne, nl));
 }
 
+} // namespace
+// the reference's own example classes (oracle/ref_examples.cpp)
+std::shared_ptr<Lpopc::FunctionWrapper> lpopc_ref_example(const std::string& name);
+namespace {
+
 shared_ptr<FunctionWrapper> make_fun(const Ref& r)
 {
+    if (r.functor.compare(0, 4, "ref:") == 0) { // "ref:<example>": the reference's own user functions
+        shared_ptr<FunctionWrapper> f = lpopc_ref_example(r.functor.substr(4));
+        if (!f) throw RefError("unknown reference example '" + r.functor + "'");
+        return f;
+    }
 #define REF_TRY(P) \
     if (r.functor == P::name()) return make_adapter<P>(r);
     LPB_FOR_EACH_PROBLEM(REF_TRY)
