@@ -13,9 +13,15 @@ collective (weak scaling: 4096 instances per GPU).
              values inside the timed region)
   roofline   k_cons_jac (dominant kernel): algorithmic bytes / CUDA-event duration vs the
              measured HBM copy bandwidth (MEASURED_PEAKS.json)
-  cpu_baseline / --impl reference: the CPU restatement of the reference path (oracle/, "port":
-             the reference itself needs Armadillo + IPOPT and cannot be compiled here) on the
-             host cores of the same box, on a bounded sample of the same workload.
+  cpu_baseline / --impl reference: the reference's OWN transcription sources on the host cores of
+             the same box (kind "reference": oracle/_ref/liblpopc_ref.so, the unmodified translation
+             units of /root/reference compiled against this repository's Armadillo stand-in
+             oracle/ref_shim/ at -O2 -- real Armadillo/BLAS and IPOPT are not in the image; one forked
+             single-threaded worker per core because the reference is not re-entrant; kind "port":
+             the oracle/ restatement, only when no oracle/_ref build exists), same workload.
+  strong     the same step on BASELINE config 4 as written: 4096 instances in TOTAL, sharded over
+             the N ranks (lpopc_b200.batch.shard_range), device-timed, max over ranks.
+  c5, hessian, hessian_probed: side measurements on rank 0 with their own roofline objects.
 """
 import argparse
 import json
@@ -69,7 +75,7 @@ def make_inputs(op, lgr_points, first, count):
 
 
 class ClockSampler:
-    """SM clock and throttle reasons DURING the timed region, polled through NVML every ~2 ms
+    """SM clock and throttle reasons DURING the timed region, polled through NVML back to back
     (same counters as the nvidia-smi clocks line of B200_PROFILING.md; nvidia-smi's own 100 ms
     period is longer than a short timed region)."""
 
@@ -102,7 +108,7 @@ class ClockSampler:
             except Exception as e:
                 self.err = repr(e)
                 return
-            time.sleep(0.002)
+            time.sleep(0)  # yield; NVML itself takes a few tens of microseconds per query
 
     def stop(self):
         if self.thread is None:
@@ -120,7 +126,7 @@ class ClockSampler:
                     reasons.add(nm)
         sm = [x for x, _ in self.samples]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(smax), "reasons": sorted(reasons),
-                "samples": len(sm), "source": "NVML polled every 2 ms inside the timed region"}
+                "samples": len(sm), "source": "NVML polled back to back inside the timed region"}
 
 
 REF_LIB = os.path.join(ROOT, "oracle", "_ref", "liblpopc_ref.so")

@@ -23,6 +23,7 @@ from oracle_lib import RefOracle  # noqa: E402
 
 GOLDEN_CASES = cases.CASES + ["launch/u5x4", "hypersensitive/u40x3", "bryson_denham/u7x6"]
 SEED = 7
+DEP_CASES = ("launch", "quadrotor", "bryson_denham", "orbit_raising", "cartpole")  # NaN dependency probe fixtures
 
 
 def main():
@@ -61,11 +62,6 @@ def main():
             for key in ("time", "state", "control", "costate", "pathmult", "hamiltonian"):
                 d["n2o_%s%d" % (key, ip)] = q[key]
             d["n2o_costs%d" % ip] = np.array([q["mayer"], q["lagrange"]])
-        if name == "launch":  # dependency probe + the sparse Hessian pattern it implies
-            d["dep"] = r.probe_dependencies(guess)
-            d["dep_info"] = np.array(r.nlp_info())
-            d["dep_hI"], d["dep_hJ"] = r.h_structure()
-            d["dep_hess"] = r.eval_h(x, sigma, lam)
         base = name.split("/")[0]
         if base in ("hypersensitive", "bryson_denham", "launch"):
             # second opinion on include/problems/<base>.h: the same transcription with the reference's OWN example
@@ -77,6 +73,11 @@ def main():
             d["refex_f"], d["refex_grad"] = np.array(r2.eval_f(x)), r2.eval_grad_f(x)
             d["refex_g"], d["refex_jac"] = r2.eval_g(x), r2.eval_jac_g(x)
             d["refex_hess"] = r2.eval_h(x, sigma, lam)
+        if name in DEP_CASES:  # dependency probe + the sparse Hessian pattern it implies
+            d["dep"] = r.probe_dependencies(guess)
+            d["dep_info"] = np.array(r.nlp_info())
+            d["dep_hI"], d["dep_hJ"] = r.h_structure()
+            d["dep_hess"] = r.eval_h(x, sigma, lam)
         path = os.path.join(out, name.replace("/", "__") + ".npz")
         np.savez_compressed(path, **d)
         print("%-28s n=%-6d m=%-6d nnz_jac=%-7d nnz_h=%-7d %6.1f KB" % ((name,) + r.nlp_info() + (os.path.getsize(path) / 1024,)))

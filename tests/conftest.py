@@ -17,3 +17,11 @@ def pytest_configure(config):
 def have_gpu():
     import torch
     return torch.cuda.is_available()
+
+
+@pytest.fixture(scope="module")
+def nlp_mod():
+    """The product's ctypes module with the CUDA library loaded (raises when liblpopc_b200.so is missing)."""
+    from lpopc_b200 import nlp
+    nlp.load_library()
+    return nlp

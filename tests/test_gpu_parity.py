@@ -1,14 +1,17 @@
 """GPU parity: the CUDA path through the C ABI vs the CPU oracle on the same seeded inputs.
 
-Bar (BASELINE.json north_star): integer triplets bit-exact; fp64 function and Jacobian values
-within 1e-12 relative of the reference restatement; Hessian (second differences divided by
-h^2 ~ 1e-12, noise-dominated) compared bit-for-bit where the arithmetic is identical and to
-1e-12 relative on the scale of the stencil noise floor otherwise (see rel_err).
+Bar (BASELINE.json north_star): integer triplets bit-exact; fp64 function, Jacobian AND Hessian values within
+1e-12 TRUE relative of the restatement (tests/parity.py: |a-b| <= 1e-12 |b| entry by entry, with the documented
+floor for entries more than ten orders below their segment's largest), and the bit-equal fraction asserted per
+quantity: user functions evaluate bit-identically on both sides, so Jacobian values are expected to be identical
+bit for bit and only the quadrature sums of f / grad f and the E-part of the Hessian may differ in the last ulp
+(measured table: profiles/r02_parity_report.txt).
 """
 import numpy as np
 import pytest
 
 import cases
+import parity
 from oracle_lib import Oracle
 
 pytestmark = pytest.mark.gpu
@@ -16,20 +19,13 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-12
 
 
-def rel_err(a, b, scale=None):
-    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
-    assert a.shape == b.shape
-    assert np.array_equal(np.isnan(a), np.isnan(b))
-    s = np.maximum(np.abs(b), 1.0) if scale is None else scale
-    d = np.abs(a - b) / s
-    return float(np.nanmax(d)) if d.size else 0.0
-
-
-@pytest.fixture(scope="module")
-def nlp_mod():
-    from lpopc_b200 import nlp
-    nlp.load_library()
-    return nlp
+def rel_err(a, b):
+    """TRUE relative error max |a-b|/|b| (tests/parity.py); inf when an entry below the documented floor of its
+    array is off by more than the floor's share of 1e-12."""
+    r = parity.report(a, b)
+    if r["max_abs_lo"] > max(parity.ATOL_LO, RTOL * parity.NOISE_FLOOR_REL) * max(r["scale"], 1e-300):
+        return float("inf")
+    return r["max_rel"]
 
 
 @pytest.mark.parametrize("name", cases.CASES + ["launch/u5x4", "hypersensitive/u40x3", "orbit_raising/u200x10"])
@@ -41,6 +37,7 @@ def test_parity_all_callbacks(nlp_mod, name):
     assert g.get_nlp_info() == (o.n, o.m, o.nnz_jac, o.nnz_h)
     gi, gj = g.eval_jac_g(values=False)
     oi, oj = o.jac_structure()
+    oi_jac = oi
     assert np.array_equal(gi, oi) and np.array_equal(gj, oj)
     gi, gj = g.eval_h(values=False)
     oi, oj = o.h_structure()
@@ -49,18 +46,16 @@ def test_parity_all_callbacks(nlp_mod, name):
         assert np.array_equal(a, b)
     guess, x, sigma, lam = cases.inputs(op, o, 7)
     for xv in (guess, x):
-        assert abs(g.eval_f(xv) - o.eval_f(xv)) <= RTOL * max(1.0, abs(o.eval_f(xv)))
-        assert rel_err(g.eval_grad_f(xv), o.eval_grad_f(xv)) <= RTOL
-        assert rel_err(g.eval_g(xv), o.eval_g(xv)) <= RTOL
-        assert rel_err(g.eval_jac_g(xv), o.eval_jac_g(xv)) <= RTOL
+        assert abs(g.eval_f(xv) - o.eval_f(xv)) <= RTOL * abs(o.eval_f(xv))
+        parity.assert_parity(g.eval_grad_f(xv), o.eval_grad_f(xv), rtol=RTOL, min_bit_equal=0.9, what="grad f")
+        parity.assert_parity(g.eval_g(xv), o.eval_g(xv), rtol=RTOL, min_bit_equal=0.999, what="g")
+        jv_g, jv_o = g.eval_jac_g(xv), o.eval_jac_g(xv)
+        for sname, idx in parity.jac_segments(op, (o.n, o.m, o.nnz_jac, o.nnz_h), oi_jac).items():
+            parity.assert_parity(jv_g[idx], jv_o[idx], rtol=RTOL, min_bit_equal=0.999, what="jac " + sname)
         gg, gv = g.eval_g_jac(xv)
-        assert np.array_equal(gg, g.eval_g(xv)) and np.array_equal(gv, g.eval_jac_g(xv))
-    # Hessian: identical arithmetic -> expect (near) bit equality; tolerance on the noise scale
-    hv_g, hv_o = g.eval_h(x, sigma, lam), o.eval_h(x, sigma, lam)
-    scale = np.maximum(np.abs(hv_o), 1.0)
-    assert rel_err(hv_g, hv_o, scale) <= 1e-9, "Hessian stencil mismatch"
-    frac_exact = float(np.mean(hv_g == hv_o))
-    assert frac_exact > 0.9, frac_exact
+        assert np.array_equal(gg, g.eval_g(xv)) and np.array_equal(gv, jv_g)
+    # Hessian: same stencil arithmetic on bit-identical function values
+    parity.assert_parity(g.eval_h(x, sigma, lam), o.eval_h(x, sigma, lam), rtol=RTOL, min_bit_equal=0.99, what="hessian")
 
 
 def test_fd_jacobian_is_bit_exact_for_polynomial_functor(nlp_mod):
@@ -85,7 +80,7 @@ def test_dependency_probe_and_sparse_hessian(nlp_mod):
     oi, oj = o.h_structure()
     assert np.array_equal(gi, oi) and np.array_equal(gj, oj)
     hv_g, hv_o = g.eval_h(x, sigma, lam), o.eval_h(x, sigma, lam)
-    assert rel_err(hv_g, hv_o) <= 1e-9
+    assert rel_err(hv_g, hv_o) <= RTOL
 
 
 def test_mesh_refresh_rebuilds_index_maps(nlp_mod):
@@ -121,9 +116,9 @@ def test_batched_instances_match_single(nlp_mod):
     og, ov = o.eval_g_jac_batch(X, nthreads=4)
     assert rel_err(G, og) <= RTOL and rel_err(V, ov) <= RTOL
     for b in (0, 17, nb - 1):
-        assert abs(F[b] - o.eval_f(X[b])) <= RTOL * max(1.0, abs(F[b]))
+        assert abs(F[b] - o.eval_f(X[b])) <= RTOL * abs(F[b])
         assert rel_err(GR[b], o.eval_grad_f(X[b])) <= RTOL
-        assert rel_err(H[b], o.eval_h(X[b], sg[b], lam[b])) <= 1e-9
+        assert rel_err(H[b], o.eval_h(X[b], sg[b], lam[b])) <= RTOL
         assert np.array_equal(G[b], g.eval_g(X[b])) and np.array_equal(V[b], g.eval_jac_g(X[b]))
 
 
@@ -174,7 +169,7 @@ def test_full_size_config2_orbit_raising_2000_nodes(nlp_mod):
     gg, gv = g.eval_g_jac(x)
     assert rel_err(gg, o.eval_g(x)) <= RTOL and rel_err(gv, o.eval_jac_g(x)) <= RTOL
     assert rel_err(g.eval_grad_f(x), o.eval_grad_f(x)) <= RTOL
-    assert rel_err(g.eval_h(x, sigma, lam), o.eval_h(x, sigma, lam)) <= 1e-9
+    assert rel_err(g.eval_h(x, sigma, lam), o.eval_h(x, sigma, lam)) <= RTOL
 
 
 @pytest.mark.gpu
@@ -189,8 +184,8 @@ def test_full_size_config3_launch_4_phases_10k_variables(nlp_mod):
     _, x, sigma, lam = cases.inputs(op, o, 4)
     gg, gv = g.eval_g_jac(x)
     assert rel_err(gg, o.eval_g(x)) <= RTOL and rel_err(gv, o.eval_jac_g(x)) <= RTOL
-    assert abs(g.eval_f(x) - o.eval_f(x)) <= RTOL * max(1.0, abs(o.eval_f(x)))
-    assert rel_err(g.eval_h(x, sigma, lam), o.eval_h(x, sigma, lam)) <= 1e-9
+    assert abs(g.eval_f(x) - o.eval_f(x)) <= RTOL * abs(o.eval_f(x))
+    assert rel_err(g.eval_h(x, sigma, lam), o.eval_h(x, sigma, lam)) <= RTOL
 
 
 @pytest.mark.gpu
@@ -219,7 +214,7 @@ def test_full_size_config4_4096_quadrotor_instances(nlp_mod):
     assert np.array_equal(G, G2) and np.array_equal(V, V2)
     F = g.eval_f_batch(X)
     for b in sample[:3]:
-        assert abs(F[b] - o.eval_f(X[b])) <= RTOL * max(1.0, abs(F[b]))
+        assert abs(F[b] - o.eval_f(X[b])) <= RTOL * abs(F[b])
 
 
 @pytest.mark.gpu
@@ -239,7 +234,44 @@ def test_full_size_config5_synthetic_100k_nodes(nlp_mod):
     gg, gv = g.eval_g_jac(x)
     assert rel_err(gg, o.eval_g(x)) <= RTOL
     assert rel_err(gv, o.eval_jac_g(x)) <= RTOL
-    assert abs(g.eval_f(x) - o.eval_f(x)) <= RTOL * max(1.0, abs(o.eval_f(x)))
+    assert abs(g.eval_f(x) - o.eval_f(x)) <= RTOL * abs(o.eval_f(x))
+
+
+@pytest.mark.gpu
+def test_full_size_config5_hessian_values_on_a_node_subsample(nlp_mod):
+    """BASELINE config 5 Hessian VALUES (76 M-nnz problem, 35.6 M-entry Hessian): the oracle needs minutes for the whole
+    mesh, so it evaluates a problem whose first 150 mesh intervals are the first 150 of the 10000-interval mesh (the
+    rest of [-1, 1] is one wide interval): on those 1500 nodes tau, w, x, u, lambda, t0, tf and sigma are the same in
+    both problems, and every per-node entry of the I-part (one N-long block per variable pair) depends on nothing
+    else -- the big problem's values at those nodes must equal the small problem's (TRUE relative 1e-12)."""
+    from lpopc_b200 import examples
+    K, Ks, Nk = 10000, 150, 10
+    op = examples.synthetic20(intervals=K, nodes=Nk)
+    g = nlp_mod.TranscribedNLP(op)
+    ops = examples.synthetic20(intervals=Ks + 1, nodes=Nk)
+    big_mesh = np.asarray(op.phases[0].meshpoints, dtype=np.float64)
+    ops.phases[0].set_mesh(np.concatenate([big_mesh[:Ks + 1], [1.0]]), [Nk] * (Ks + 1))
+    o = Oracle(ops)
+    ns, nc = 20, 6
+    N, Ns, M = K * Nk, (Ks + 1) * Nk, Ks * Nk
+    x = _seeded_x(g, 11)[0]
+    x[-2], x[-1] = 0.0, 10.0
+    rng = np.random.Generator(np.random.PCG64(12))
+    lam = rng.uniform(-1, 1, g.m)
+    xs, lams = np.zeros(o.n), np.zeros(o.m)
+    for j in range(ns):
+        xs[j * (Ns + 1):j * (Ns + 1) + M] = x[j * (N + 1):j * (N + 1) + M]
+        lams[j * Ns:j * Ns + M] = lam[j * N:j * N + M]
+    for j in range(nc):
+        xs[ns * (Ns + 1) + j * Ns:ns * (Ns + 1) + j * Ns + M] = x[ns * (N + 1) + j * N:ns * (N + 1) + j * N + M]
+    xs[-2], xs[-1] = x[-2], x[-1]
+    hb, hs = g.eval_h(x, 0.75, lam), o.eval_h(xs, 0.75, lams)
+    nblk = (ns + nc) * (ns + nc + 1) // 2  # dense pattern: xx / ux / uu blocks, then the t0 and tf row blocks
+    nrow = nblk + 2 * (ns + nc)
+    big = np.stack([hb[b * N + (1 if b >= nblk + ns + nc else 0):][:M] for b in range(nrow)])
+    small = np.stack([hs[b * Ns + (1 if b >= nblk + ns + nc else 0):][:M] for b in range(nrow)])
+    r = parity.assert_parity(big, small, rtol=RTOL, min_bit_equal=0.99, what="config 5 Hessian, first 1500 nodes")
+    assert r["n"] == nrow * M and r["scale"] > 0
 
 
 @pytest.mark.parametrize("name", ["synthetic20", "synthetic20/ragged", "synthetic20/u50x10"])
