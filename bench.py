@@ -42,9 +42,13 @@ SOLVE_INSTANCES = 4096  # per GPU, for the solves/s side measurement
 MESH_INTERVALS, MESH_NODES = 8, 8
 NBUF = 4  # rotating input sets so that x is not served from L2 between steps
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_cons_jac launch of this workload (4096 instances)
-# from the committed `ncu --set full` capture (profiles/r01_cons_jac_full.txt: 35.76 MB read + 622.69 MB
-# written; below the 713 MB algorithmic figure because part of the last stores is still in L2 at kernel end)
+# from the committed `ncu --set full` capture (35.76 MB read + 622.69 MB written; below the 713 MB algorithmic figure
+# because part of the last stores is still in L2 at kernel end).  DRAM counters cannot be read outside a profiler, so
+# this is NOT measured in the bench run; the line says where it comes from.
 NCU_TRAFFIC_BYTES = 658450944
+NCU_TRAFFIC_SOURCE = "profiles/r01_cons_jac_full.txt (ncu --set full of this kernel on this workload; not measured in this run)"
+STRONG_TOTAL = 4096  # BASELINE config 4 as written: 4096 instances in total, sharded over the ranks
+C5_INTERVALS, C5_NODES = 10000, 10  # BASELINE config 5: synthetic ns=20 / nc=6 dynamics on 100k LGR nodes
 
 
 def quadrotor_problem():
@@ -158,8 +162,14 @@ class CpuPath:
         from oracle_lib import Oracle
         self.nnz = Oracle(op).nnz_jac
         self.kind = "reference" if os.path.exists(REF_LIB) else "port"
+        self.lib = None
         if self.kind == "reference":
+            import hashlib
             import multiprocessing as mp
+            from oracle_lib import ref_lib
+            ref_lib()  # dlopen in THIS process too (the forked workers inherit the mapping): the library that is timed
+            self.lib = {"path": os.path.relpath(REF_LIB, ROOT), "sha256": hashlib.sha256(open(REF_LIB, "rb").read()).hexdigest(),
+                        "built_from": "/root/reference/Lpopc/src (unmodified translation units) + oracle/ref_shim (Armadillo stand-in), g++ -O2, oracle/ref_build.mk"}
             _worker["X"] = X  # inherited by the forked workers
             self.pool = mp.get_context("fork").Pool(threads, initializer=_ref_worker_init)
             per = (len(X) + threads - 1) // threads
@@ -177,6 +187,12 @@ class CpuPath:
         if self.kind == "reference":
             self.pool.close()
             self.pool.join()
+
+    def baseline(self, value, threads, sample):
+        d = {"value": value, "unit": "nnz/s", "cores": threads, "kind": self.kind, "sample": sample}
+        if self.lib:
+            d["library"] = self.lib
+        return d
 
     def describe(self):
         if self.kind == "reference":
@@ -223,13 +239,27 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "collocation Jacobian nnz/s", "value": value, "unit": "nnz/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(o, world, sample_note="all %d instances of one GPU's share per step, on the host" % sample),
-        "cpu_baseline": {"value": value, "unit": "nnz/s", "cores": threads, "kind": cp.kind,
-                         "sample": "%d of %d quadrotor instances per step; %s" % (sample, INSTANCES_PER_GPU, cp.describe())},
+        "config": workload_config(o, world),
+        "cpu_baseline": cp.baseline(value, threads, "all %d quadrotor instances of one GPU's share per step, on the host; %s" % (sample, cp.describe())),
         "e2e": {"value": value, "unit": "nnz/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+def hbm_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback 6650 GB/s (B200_PROFILING.md)"
+
+
+def hbm_roofline(algorithmic_bytes, ms):
+    """roofline object of a side measurement: algorithmic bytes per evaluation / device time against the HBM peak."""
+    peak, src = hbm_peak()
+    ach = algorithmic_bytes / (ms * 1e-3) / 1e9
+    return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "bytes": algorithmic_bytes, "peak_source": src,
+            "traffic": None}
 
 
 class _Sizes:
@@ -237,14 +267,12 @@ class _Sizes:
         self.n, self.m, self.nnz_jac, self.nnz_h = n, m, nnz_jac, nnz_h
 
 
-def workload_config(o, world, sample_note=None):
+def workload_config(o, world):
     cfg = {"workload": "batched quadrotor MPC (BASELINE config 4): %d OCP instances per GPU, shared %dx%d LGR mesh, "
                        "fused eval_g+eval_jac_g by forward differences" % (INSTANCES_PER_GPU, MESH_INTERVALS, MESH_NODES),
            "instances_per_gpu": INSTANCES_PER_GPU, "instances_total": INSTANCES_PER_GPU * world,
            "n": o.n, "m": o.m, "nnz_jac": o.nnz_jac, "nnz_h": o.nnz_h, "parallelism": "instances sharded x%d, no data-path collective" % world,
            "l2": "%d rotating input sets + %.0f MB written per step (> 126 MB L2)" % (NBUF, 8e-6 * INSTANCES_PER_GPU * (o.m + o.nnz_jac))}
-    if sample_note:
-        cfg["sample"] = sample_note
     return cfg
 
 
@@ -257,6 +285,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip the Hessian / large-mesh side measurements")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--dense-return", action="store_true", help="e2e: return the whole Jacobian head over PCIe (sparse_return = 0)")
+    ap.add_argument("--no-persistent", action="store_true", help="e2e: the host rewrites the constant tail and the zero fill on every call")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -336,9 +365,19 @@ def main():
     for k in range(args.warmup):
         step(k)
     barrier()
-    g.set_option("time_kernels", 1)
     sampler = ClockSampler(local_rank)
     sampler.start()
+    # clock window: one NVML query takes milliseconds, the K timed steps a few, so the sampler also watches the same
+    # step running back to back (untimed) right before the timed region, until it holds >= 60 samples
+    window_steps = 0
+    t_w = time.perf_counter()
+    while len(sampler.samples) < 60 and time.perf_counter() - t_w < 3.0 and sampler.thread is not None:
+        for k in range(50):
+            step(k)
+        torch.cuda.synchronize()
+        window_steps += 50
+    in_window = len(sampler.samples)
+    g.set_option("time_kernels", 1)
     l0 = g.kernel_launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -352,6 +391,8 @@ def main():
     kern_ms, kern_cnt = g.kernel_time("cons_jac")
     g.set_option("time_kernels", 0)
     clocks = sampler.stop()
+    clocks["samples_in_timed_region"] = max(0, clocks.get("samples", 0) - in_window)
+    clocks["window"] = "%d untimed steps of the same kernel back to back immediately before the %d timed steps, then the timed steps" % (window_steps, args.steps)
     tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -365,7 +406,10 @@ def main():
     e2e_steps = max(3, min(args.steps, 10))
     if args.dense_return:
         g.set_option("sparse_return", 0)
-    for k in range(2):
+    # the caller (like IPOPT's TNLPAdapter) hands the same values array to every call and leaves it alone in
+    # between: constant tail and zero fill stay in place, the host threads write nothing after the second call
+    g.set_option("persistent_values", 0 if args.no_persistent else 1)
+    for k in range(3):
         g.eval_g_jac_batch_ptr(nb, hx[k % 2].data_ptr(), hg.data_ptr(), hv.data_ptr())
     barrier()
     t0 = time.perf_counter()
@@ -378,6 +422,24 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = nnz * nb * world * e2e_steps / float(te.item())
     sparse_calls, sparse_on, sparse_fixups = g.stat("sparse_calls"), g.stat("sparse_on_doubles"), g.stat("sparse_fixups")
+    persistent_hits = g.stat("persistent_hits")
+    # PCIe floor of that call: one D2H copy of the bytes it returns (pinned), H2D of x in the other direction alongside
+    d2h_bytes = 8 * nb * (m + (sparse_on if sparse_calls else nnz))
+    probe_src = torch.empty(d2h_bytes // 8, dtype=torch.float64, device=dev)
+    probe_dst = torch.empty(d2h_bytes // 8, dtype=torch.float64).pin_memory()
+    side = torch.cuda.Stream()
+    probe_dst.copy_(probe_src, non_blocking=True)
+    torch.cuda.synchronize()
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pe0.record()
+    for k in range(3):
+        with torch.cuda.stream(side):
+            xs[0].copy_(hx[k % 2], non_blocking=True)
+        probe_dst.copy_(probe_src, non_blocking=True)
+    pe1.record()
+    torch.cuda.synchronize()
+    pcie_ms = pe0.elapsed_time(pe1) / 3
+    del probe_src, probe_dst
     # the host-pointer call must deliver exactly what the device-resident call computes
     chk = torch.from_numpy(X + 1e-3 * ((e2e_steps - 1) % 2)).to(dev)
     g.eval_g_jac_dev(nb, chk.data_ptr(), d_g.data_ptr(), d_v.data_ptr())
@@ -391,6 +453,43 @@ def main():
     g.eval_f_dev(nb, xs[0].data_ptr(), d_f.data_ptr())
     torch.cuda.synchronize()
     all_f = batch.gather_results(d_f.cpu().numpy(), nb * world, dist if world > 1 else None, dev)
+
+    # ---- BASELINE config 4 as written: STRONG_TOTAL instances in total, sharded over the ranks ----
+    slo, shi = batch.shard_range(STRONG_TOTAL, rank, world)
+    snb = shi - slo
+    sX = make_inputs(op, pts, slo, snb) if world > 1 else X
+    sxs = [torch.from_numpy(sX + 1e-3 * k).to(dev) for k in range(NBUF)] if world > 1 else xs
+    for k in range(args.warmup):
+        g.eval_g_jac_dev(snb, sxs[k % NBUF].data_ptr(), d_g.data_ptr(), d_v.data_ptr())
+    barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for k in range(args.steps):
+        g.eval_g_jac_dev(snb, sxs[k % NBUF].data_ptr(), d_g.data_ptr(), d_v.data_ptr())
+    s1.record()
+    barrier()
+    tsm = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device=dev)
+    # the same shard through the host-pointer call
+    shx = [torch.from_numpy(sX + 1e-3 * k).pin_memory() for k in range(2)] if world > 1 else hx
+    for k in range(3):
+        g.eval_g_jac_batch_ptr(snb, shx[k % 2].data_ptr(), hg.data_ptr(), hv.data_ptr())
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        g.eval_g_jac_batch_ptr(snb, shx[k % 2].data_ptr(), hg.data_ptr(), hv.data_ptr())
+    barrier()
+    tse = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tsm, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tse, op=dist.ReduceOp.MAX)
+    strong = {"scaling": "strong", "instances_total": STRONG_TOTAL, "instances_per_gpu": snb,
+              "value": nnz * STRONG_TOTAL * args.steps / (float(tsm.item()) * 1e-3), "unit": "nnz/s",
+              "ms_per_step": float(tsm.item()) / args.steps,
+              "hbm_frac_per_gpu": 8 * snb * (n + m + nnz) / (float(tsm.item()) / args.steps * 1e-3) / 1e9 / hbm_peak()[0],
+              "e2e": {"value": nnz * STRONG_TOTAL * e2e_steps / float(tse.item()), "unit": "nnz/s", "ms_per_step": 1e3 * float(tse.item()) / e2e_steps},
+              "note": "device-timed like `value` (CUDA events, max over ranks); shards are contiguous blocks of ceil(4096/N) instances "
+                      "(lpopc_b200.batch.shard_range), no data-path collective"}
+    del sxs, shx
 
     extras = {}
     if not args.no_extras and rank == 0:
@@ -410,8 +509,39 @@ def main():
         torch.cuda.synchronize()
         hms = h0.elapsed_time(h1) / hs
         extras["hessian"] = {"value": nnz_h * nb / (hms * 1e-3), "unit": "nnz_h/s", "ms_per_eval": hms,
-                             "bytes_per_eval": 8 * nb * (n + m + nnz_h)}
+                             "bytes_per_eval": 8 * nb * (n + m + nnz_h), "kernel": "k_hess_tiled<LpbQuadrotor,6,3> + k_hess_endpoint",
+                             "roofline": hbm_roofline(8 * nb * (n + m + nnz_h), hms)}
         del lam, d_h
+        # BASELINE config 5: one synthetic ns=20 / nc=6 problem on 100k LGR nodes (76 M nnz), fused eval_g + eval_jac_g
+        from lpopc_b200 import examples as _ex
+        g5 = nlp.TranscribedNLP(_ex.synthetic20(intervals=C5_INTERVALS, nodes=C5_NODES))
+        g5.set_stream(torch.cuda.current_stream().cuda_stream)
+        n5, m5, nnz5, _ = g5.get_nlp_info()
+        r5 = np.random.Generator(np.random.PCG64(7))
+        x5 = r5.uniform(-1.0, 1.0, n5)
+        x5[-2], x5[-1] = 0.0, 10.0
+        x5s = [torch.from_numpy(x5 + 1e-3 * k).to(dev) for k in range(2)]
+        g5_g = torch.empty(m5, dtype=torch.float64, device=dev)
+        g5_v = torch.empty(nnz5, dtype=torch.float64, device=dev)
+        for k in range(3):
+            g5.eval_g_jac_dev(1, x5s[k % 2].data_ptr(), g5_g.data_ptr(), g5_v.data_ptr())
+        torch.cuda.synchronize()
+        g5.set_option("time_kernels", 1)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c5_steps = 10
+        c0.record()
+        for k in range(c5_steps):
+            g5.eval_g_jac_dev(1, x5s[k % 2].data_ptr(), g5_g.data_ptr(), g5_v.data_ptr())
+        c1.record()
+        torch.cuda.synchronize()
+        c5ms = c0.elapsed_time(c1) / c5_steps
+        k5ms, k5cnt = g5.kernel_time("cons_jac")
+        g5.set_option("time_kernels", 0)
+        extras["c5"] = {"workload": "BASELINE config 5: synthetic ns=20/nc=6 dynamics, %d x %d = %d LGR nodes, one problem, fused eval_g+eval_jac_g"
+                                    % (C5_INTERVALS, C5_NODES, C5_INTERVALS * C5_NODES),
+                        "n": n5, "m": m5, "nnz_jac": nnz5, "ms_per_step": c5ms, "value": nnz5 / (c5ms * 1e-3), "unit": "nnz/s",
+                        "kernel_ms": k5ms / max(1, k5cnt), "roofline": hbm_roofline(8 * (n5 + m5 + nnz5), c5ms)}
+        del g5, g5_g, g5_v, x5s
 
     solves = None
     if not args.no_extras:
@@ -444,7 +574,7 @@ def main():
             torch.cuda.synchronize()
             pms = p0.elapsed_time(p1) / 5
             extras["hessian_probed"] = {"value": nh2 * nb / (pms * 1e-3), "unit": "nnz_h/s", "nnz_h": nh2, "ms_per_eval": pms,
-                                        "bytes_per_eval": 8 * nb * (n + m + nh2)}
+                                        "bytes_per_eval": 8 * nb * (n + m + nh2), "roofline": hbm_roofline(8 * nb * (n + m + nh2), pms)}
             del lam2, sg2, d_h2
         bxl, bxu, _, _ = ev.bounds()
         XL, XU = batch.mpc_bounds(bxl, bxu, op, x0s)
@@ -509,6 +639,10 @@ def main():
                     "steps": e2e_steps, "ms_per_step": 1e3 * float(te.item()) / e2e_steps, "host_buffers": "pinned", "cpu_affinity": affinity,
                     "sparse_return": {"calls": sparse_calls, "values_sent_per_instance": sparse_on, "head_values_per_instance": nnz - const_tail,
                                       "segments_refetched": sparse_fixups},
+                    "persistent_values": {"enabled": not args.no_persistent, "calls_without_host_writes": persistent_hits},
+                    "pcie_floor": {"d2h_bytes": d2h_bytes, "ms": pcie_ms, "gbs": d2h_bytes / (pcie_ms * 1e-3) / 1e9,
+                                   "how": "one pinned D2H cudaMemcpy of the bytes the call returns, with the H2D of x on a second stream, "
+                                          "CUDA events, rank 0, after the timed e2e region"},
                     "note": "all nnz_jac values are delivered per call and checked against the device-resident evaluation; the %d "
                             "mesh-constant values per instance (linear rows + Doffdiag segment) are written into the caller's array by host "
                             "threads from a cached copy, and of the %d x-dependent values only the (row block, column block) segments that "
@@ -516,15 +650,15 @@ def main():
                             "host threads)" % (const_tail, nnz - const_tail)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_cons_jac<LpbQuadrotor,WANT_G=1,WANT_JAC=1,UNROLL=1>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES, "bytes_per_launch": kbytes, "avg_launch_ms": kavg_ms,
+                         "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES, "traffic_source": NCU_TRAFFIC_SOURCE, "bytes_per_launch": kbytes, "avg_launch_ms": kavg_ms,
                          "launches_timed": kern_cnt, "peak_source": peak_src,
                          "step_bytes": 8 * nb * (n + m + nnz), "step_frac": 8 * nb * (n + m + nnz) / (ms / args.steps * 1e-3) / 1e9 / peak},
-            "cpu_baseline": ({"value": cpu[0], "unit": "nnz/s", "cores": threads, "kind": cpu[3].kind,
-                              "sample": "all %d quadrotor instances x %d passes in %.1f s; %s" % (nb, cpu[2], cpu[1], cpu[3].describe())}
+            "cpu_baseline": (cpu[3].baseline(cpu[0], threads, "all %d quadrotor instances x %d passes in %.1f s; %s" % (nb, cpu[2], cpu[1], cpu[3].describe()))
                              if cpu else {"value": None, "unit": "nnz/s", "cores": threads, "kind": "skipped (--no-cpu)", "sample": ""}),
             "objective_checksum": float(np.sum(all_f)),
         }
         line.update(extras)
+        line["strong"] = strong
         if solves:
             line["solves"] = solves
         sys.stdout.flush()

@@ -407,6 +407,18 @@ struct lpb_handle {
     DevBuf<unsigned char> d_seg_on;
     int* h_seg_flags = nullptr; // pinned
     long long sparse_calls = 0, sparse_fixups = 0;
+    // option "persistent_values": the caller hands the SAME values array to consecutive batch calls and does not
+    // write to it in between (IPOPT's TNLPAdapter does exactly that with its jac_g array).  Everything the host
+    // threads would write on the sparse path -- the constant tail and the fill pattern of the off-segments -- is
+    // then already in place from the previous call, so they write nothing and only the on-segments cross PCIe.
+    // What was written is remembered as (array, batch size, plan version); two sentinel values per instance (first
+    // constant-tail value, first value of the first fill run) are re-read on every call and any mismatch -- a new
+    // or overwritten array -- falls back to the full fill.
+    int persistent_values = 0;
+    const double* filled_values = nullptr;
+    int filled_nbatch = 0;
+    long long filled_plan = -1, plan_version = 0;
+    long long persistent_hits = 0;
     lpb_handle() { std::memset(&pd, 0, sizeof pd); std::memset(&lay, 0, sizeof lay); std::memset(&ltab, 0, sizeof ltab); std::memset(&opts, 0, sizeof opts); }
     ~lpb_handle()
     {
@@ -591,6 +603,7 @@ static void refresh(lpb_handle* h)
         h->seg_on.assign(h->seg_off.size(), 0);
         h->seg_fill.assign(h->seg_off.size(), 0LL);
         h->seg_mask_init = false;
+        ++h->plan_version;
         h->d_seg_off.upload(h->seg_off, h->stream);
         h->d_seg_len.upload(h->seg_len, h->stream);
         h->d_seg_on.upload(h->seg_on, h->stream);
@@ -610,6 +623,7 @@ static void rebuild_sparse_plan(lpb_handle* h)
     const size_t nseg = h->seg_off.size();
     h->fill_runs.clear();
     h->on_doubles = 0;
+    ++h->plan_version; // whatever an earlier call left in a caller's array no longer matches the plan
     for (size_t s = 0; s < nseg; ++s) {
         if (!h->seg_maskable[s]) h->seg_on[s] = 1;
         if (h->seg_on[s]) { h->on_doubles += (size_t)h->seg_len[s]; continue; }
@@ -1057,7 +1071,18 @@ int lpb_eval_g_jac_batch(lpb_handle* h, int nbatch, const double* x, double* g, 
     const bool sparse = values_dev && h->seg_mask_init && h->on_doubles * 4 <= head * 3;
     const bool flags_wanted = learn || sparse;
     std::vector<std::thread> th;
-    if (host_tail && !(h->debug_skip & 1)) {
+    bool in_place = false; // persistent_values: tail and fill patterns are still in the caller's array
+    if (sparse && h->persistent_values && h->filled_values == values && h->filled_nbatch == nbatch && h->filled_plan == h->plan_version) {
+        in_place = true;
+        const long long t0 = *reinterpret_cast<const long long*>(h->h_ctail.data());
+        for (int b = 0; b < nbatch && in_place; ++b) {
+            const long long* vb = reinterpret_cast<const long long*>(values + (size_t)b * nnz);
+            if (vb[head] != t0) in_place = false;
+            if (!h->fill_runs.empty() && vb[h->fill_runs[0].off] != h->fill_runs[0].bits) in_place = false;
+        }
+        if (in_place) ++h->persistent_hits;
+    }
+    if (host_tail && !(h->debug_skip & 1) && !in_place) {
         unsigned hw = std::thread::hardware_concurrency();
         int nt = (int)(hw > 1 ? hw / 2 : 1); // half the hardware threads: the rest is left to the driver and the caller
         if (nt > 16) nt = 16;
@@ -1148,6 +1173,7 @@ int lpb_eval_g_jac_batch(lpb_handle* h, int nbatch, const double* x, double* g, 
             changed = true;
         }
         if (sparse) ++h->sparse_calls;
+        if (sparse && !changed) { h->filled_values = values; h->filled_nbatch = nbatch; h->filled_plan = h->plan_version; }
         if (changed) {
             h->seg_mask_init = true;
             rebuild_sparse_plan(h); // synchronises the stream: the fix-up copies have landed
@@ -1427,6 +1453,7 @@ int lpb_set_option_int(lpb_handle* h, const char* name, int value)
     else if (!std::strcmp(name, "host_fill_const")) h->host_fill_const = value;
     else if (!std::strcmp(name, "host_threads")) h->host_threads = value;
     else if (!std::strcmp(name, "sparse_return")) h->sparse_return = value;
+    else if (!std::strcmp(name, "persistent_values")) { h->persistent_values = value; h->filled_values = nullptr; }
     else if (!std::strcmp(name, "debug_skip")) h->debug_skip = value;
     else if (!std::strcmp(name, "auto_pin")) {
         h->auto_pin = value;
@@ -1477,6 +1504,7 @@ int lpb_get_stat(lpb_handle* h, const char* name, long long* value)
     else if (!std::strcmp(name, "sparse_fixups")) *value = h->sparse_fixups;
     else if (!std::strcmp(name, "sparse_on_doubles")) *value = h->seg_mask_init ? (long long)h->on_doubles : -1;
     else if (!std::strcmp(name, "head_doubles")) *value = (long long)h->pd.lin_val0;
+    else if (!std::strcmp(name, "persistent_hits")) *value = h->persistent_hits;
     else if (!std::strncmp(name, "hess_I0.", 8) || !std::strncmp(name, "hess_E0.", 8) || !std::strncmp(name, "hess_L0.", 8)) {
         // first Hessian value of the I-part / E-part of phase <p>, of the link part of pair <q> (parity reports by segment)
         need_fresh(h);
