@@ -42,6 +42,17 @@
  *     k.path_row(cc, i, cp, path[i])
  * once per row.  The values passed must be exactly what dae() returns at the perturbed point (same operations,
  * same order); the kernels do the quotients and the scatter.  Without the hook the kernels call dae() per colour.
+ *
+ * Optional members `sweep_pre` / `sweep_row` (flagged by `static constexpr bool HAS_ROW_SWEEP = true`, with
+ * `ROW_SWEEP_PRE` = doubles per variable): the same sweep split over the function rows, for dynamics whose rows read
+ * most variables.  The kernel (k_cons_jac_rows) runs one warp per row over 32 nodes:
+ *     static void sweep_pre(c, phase, cc, v, vp, double* pre, int stride)
+ * once per (node, variable cc): v = the variable's value, vp = v + h; stores up to ROW_SWEEP_PRE values of that
+ * variable at pre[0], pre[stride], ... (e.g. an expensive elementary function at v and at vp);
+ *     template <class ND, class K> static double sweep_row(c, phase, s, const ND& nd, K& k)
+ * once per (node, row s in [0, NS + NPATH)): nd.x(j), nd.u(j), nd.t the node's variables, nd.perturbed(cc) = vp of
+ * variable cc, nd.pre(cc, i) the values sweep_pre stored; k as in dae_sweep (begin / state_row / path_row for row s
+ * only).  Returns the row's base value f_s (path rows: the path value).  Same exactness contract as dae_sweep.
  */
 #ifndef LPB_FUNCTOR_H
 #define LPB_FUNCTOR_H

@@ -88,6 +88,73 @@ struct LpbSynthetic20 {
 #pragma unroll 1
         for (int s = 0; s < NS; ++s) k.state_row(NS + NC, s, f[s], f[s]);
     }
+    /* Optional hooks (lpb_functor.h "row-parallel sweep"): the same sweep split over the rows.  sweep_pre runs once
+     * per (node, variable) and parks what every row needs of that variable -- tanh at the base and at the perturbed
+     * value -- and sweep_row runs once per (node, row s): the row's 26 products A_sq tanh(x_q), B_sq u_q stay in
+     * registers, a perturbed state j re-adds the terms from j onwards in dae()'s order, nothing is recomputed per
+     * row.  Bit-identical to dae() column by column, like dae_sweep. */
+    static constexpr bool HAS_ROW_SWEEP = true;
+    static constexpr int ROW_SWEEP_PRE = 2;
+#ifndef LPB_S20_ROW_LO
+#define LPB_S20_ROW_LO 13
+#endif
+#ifdef LPB_S20_REGS
+    static constexpr int ROW_SWEEP_REGS = LPB_S20_REGS;
+#endif
+    static constexpr int ROW_LO = LPB_S20_ROW_LO;     /* products q < ROW_LO live in the thread's shared-memory scratch */
+    static constexpr int ROW_SWEEP_SCRATCH = ROW_LO;  /* (they are re-added by few colours), the rest in registers */
+    LPB_HD static void sweep_pre(const Consts&, int, int cc, double v, double vp, double* pre, int stride)
+    {
+        if (cc < NS) {
+            pre[0] = lpb_det_tanh(v);
+            pre[stride] = lpb_det_tanh(vp);
+        }
+    }
+    template <class ND, class K>
+    LPB_HD static double sweep_row(const Consts& C, int, int s, const ND& nd, K& k)
+    {
+        double pr[NS + NC - ROW_LO]; /* pr[q - ROW_LO] = q-th product of the row sum, q >= ROW_LO */
+        double acc = 0.0;
+#pragma unroll
+        for (int q = 0; q < NS; ++q) {
+            const double prod = C.A[s * NS + q] * nd.pre(q, 0);
+            if (q < ROW_LO) nd.scratch(q) = prod;
+            else pr[q - ROW_LO] = prod;
+            acc = acc + prod;
+        }
+#pragma unroll
+        for (int q = 0; q < NC; ++q) {
+            const double prod = C.B[s * NC + q] * nd.u(q);
+            pr[NS + q - ROW_LO] = prod;
+            acc = acc + prod;
+        }
+        const double xs = nd.x(s);
+        const double cube = 0.1 * ((xs * xs) * xs);
+        const double fs = acc - cube;
+        const double xsp = nd.perturbed(s); /* the only colour whose cubic term differs is j == s */
+        const double cubep = 0.1 * ((xsp * xsp) * xsp);
+        double pre = 0.0;
+#pragma unroll
+        for (int j = 0; j < NS; ++j) { /* state colours */
+            k.begin(j, 0.0);
+            double a2 = pre + C.A[s * NS + j] * nd.pre(j, 1);
+#pragma unroll
+            for (int q = j + 1; q < NS + NC; ++q) a2 = a2 + (q < ROW_LO ? nd.scratch(q) : pr[q < ROW_LO ? 0 : q - ROW_LO]);
+            k.state_row(j, s, a2 - (s == j ? cubep : cube), fs);
+            pre = pre + (j < ROW_LO ? nd.scratch(j) : pr[j < ROW_LO ? 0 : j - ROW_LO]);
+        }
+#pragma unroll
+        for (int j = 0; j < NC; ++j) { /* control colours: pre now holds the whole state sum */
+            const double vp = k.begin(NS + j, 0.0);
+            double a2 = pre;
+#pragma unroll
+            for (int q = 0; q < NC; ++q) a2 = a2 + (q == j ? C.B[s * NC + q] * vp : pr[NS + q - ROW_LO]);
+            k.state_row(NS + j, s, a2 - cube, fs);
+        }
+        k.begin(NS + NC, 0.0); /* time colour: dae() does not read t */
+        k.state_row(NS + NC, s, fs, fs);
+        return fs;
+    }
     LPB_HD static double lagrange(const Consts&, int, double, const double* x, const double* u)
     {
         double acc = 0.0;

@@ -1472,6 +1472,7 @@ int lpb_set_option_int(lpb_handle* h, const char* name, int value)
     }
     else if (!std::strcmp(name, "unroll_colours")) h->opts.unroll_colours = value;
     else if (!std::strcmp(name, "hess_variant")) h->opts.hess_variant = value;
+    else if (!std::strcmp(name, "sweep_mode")) h->opts.sweep_mode = value;
     else if (!std::strcmp(name, "rotate_nodes")) h->opts.no_rotate = value ? 0 : 1;
     else if (!std::strcmp(name, "stage_values")) h->opts.stage_values = value;
     else if (!std::strcmp(name, "time_kernels")) h->time_kernels = value != 0;

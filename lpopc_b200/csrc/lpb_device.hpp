@@ -98,6 +98,7 @@ struct LaunchOpts {
     int no_rotate;      // 1: do not rotate the thread -> node map of the Jacobian kernel (A/B measurement)
     int unroll_colours; // Jacobian kernel variant: -1 = functor default (P::UNROLL_COLOURS), 0 = colour loop, 1 = unrolled;
                         // Hessian node kernel: 0 = generic pair loops, otherwise the tiled kernel where the functor set has HESS_DEP
+    int sweep_mode;     // Jacobian kernel of functor sets with sweep hooks: 0 = row-parallel sweep where available, 1 = per-thread sweep
     int hess_variant;   // tuning builds (-DLPB_HESS_VARIANTS): (tile size, CTAs/SM) instantiation of the tiled Hessian kernel
     // optional CUDA events recorded on the launch stream right before / after the dominant
     // node kernel (bench.py's live roofline measurement); null = no timing

@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--stage", type=int, nargs="*", default=[0], help="shared-memory staged write-out of the Jacobian values (where it applies)")
     ap.add_argument("--rotate", type=int, nargs="*", default=[1], help="thread -> node rotation of the Jacobian kernel (aligned stores)")
+    ap.add_argument("--sweep-mode", type=int, nargs="*", default=[0], help="functor sets with sweep hooks: 0 row-parallel (default row warps), 1 per-thread, 2 / 3 other row-warp counts")
     ap.add_argument("--hessian", action="store_true")
     ap.add_argument("--fg", action="store_true", help="also time eval_f and eval_grad_f")
     ap.add_argument("--pair-split", type=int, nargs="*", default=[0])
@@ -56,8 +57,9 @@ def main():
     d_v = torch.empty((nb, nnz), dtype=torch.float64, device="cuda")
     step_bytes = 8 * nb * (n + m + nnz)
     print("problem %s nb=%d n=%d m=%d nnz_jac=%d nnz_h=%d step_bytes=%.1f MB" % (args.problem, nb, n, m, nnz, nnz_h, step_bytes / 1e6))
-    for un, rot, stg in [(u, r, s_) for u in args.unroll for r in args.rotate for s_ in args.stage]:
+    for un, rot, stg, swm in [(u, r, s_, w) for u in args.unroll for r in args.rotate for s_ in args.stage for w in args.sweep_mode]:
         for sp in args.split:
+            g.set_option("sweep_mode", swm)
             g.set_option("unroll_colours", un)
             g.set_option("rotate_nodes", rot)
             g.set_option("stage_values", stg)
@@ -75,8 +77,8 @@ def main():
             ms = e0.elapsed_time(e1) / args.steps
             kms, kc = g.kernel_time("cons_jac")
             g.set_option("time_kernels", 0)
-            print("unroll=%2d rotate=%d stage=%d split=%2d  step %.4f ms (%.1f%% hbm, %.3e nnz/s)  k_cons_jac %.4f ms" %
-                  (un, rot, stg, sp, ms, 100 * step_bytes / (ms * 1e-3) / 1e9 / peak, nnz * nb / (ms * 1e-3), kms / max(kc, 1)))
+            print("unroll=%2d rotate=%d stage=%d sweep_mode=%d split=%2d  step %.4f ms (%.1f%% hbm, %.3e nnz/s)  k_cons_jac %.4f ms" %
+                  (un, rot, stg, swm, sp, ms, 100 * step_bytes / (ms * 1e-3) / 1e9 / peak, nnz * nb / (ms * 1e-3), kms / max(kc, 1)))
     if args.fg:
         d_f = torch.empty(nb, dtype=torch.float64, device="cuda")
         d_gr = torch.empty((nb, n), dtype=torch.float64, device="cuda")

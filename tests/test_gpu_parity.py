@@ -274,25 +274,44 @@ def test_full_size_config5_hessian_values_on_a_node_subsample(nlp_mod):
     assert r["n"] == nrow * M and r["scale"] > 0
 
 
-@pytest.mark.parametrize("name", ["synthetic20", "synthetic20/ragged", "synthetic20/u50x10"])
+@pytest.mark.parametrize("name", ["synthetic20", "synthetic20/ragged", "synthetic20/u50x10", "synthetic20/u7x9"])
 def test_dae_sweep_hook_is_bit_identical(nlp_mod, name):
-    """Functor sets with the optional dae_sweep hook (include/lpb_functor.h): the one-pass sweep must hand the
-    kernel exactly the values dae() returns column by column -- Jacobian values and constraints bit-identical
-    to the plain colour loop on the device, and within 1e-12 of the oracle (which has no sweep)."""
+    """Functor sets with the optional sweep hooks (include/lpb_functor.h): the one-pass per-thread sweep (dae_sweep) and
+    the row-parallel sweep (sweep_pre / sweep_row, one warp per function row) must hand the kernel exactly the values
+    dae() returns column by column -- Jacobian values and constraints bit-identical to the plain colour loop on the
+    device, single problems and batches, and within 1e-12 of the oracle (which has no sweep)."""
     op = cases.build(name)
     o = Oracle(op)
     g = nlp_mod.TranscribedNLP(op)
     _, x, _, _ = cases.inputs(op, o, 21)
-    g.set_option("colour_split", 1)      # whole colour range in one thread: the sweep kernel
-    g_s, v_s = g.eval_g_jac(x)
+    l0 = g.kernel_launches
+    g_r, v_r = g.eval_g_jac(x)           # default: row-parallel sweep
     v_only = g.eval_jac_g(x)
+    assert g.kernel_launches > l0
+    g.set_option("sweep_mode", 1)        # per-thread sweep (whole colour range in one thread)
+    g.set_option("colour_split", 1)
+    g_s, v_s = g.eval_g_jac(x)
     g.set_option("unroll_colours", 0)    # forces the plain colour loop
     g_p, v_p = g.eval_g_jac(x)
-    assert np.array_equal(v_s.view(np.int64), v_p.view(np.int64))
-    assert np.array_equal(v_only.view(np.int64), v_p.view(np.int64))
-    assert np.array_equal(g_s.view(np.int64), g_p.view(np.int64))
-    assert rel_err(v_s, o.eval_jac_g(x)) <= RTOL
-    assert rel_err(g_s, o.eval_g(x)) <= RTOL
+    for v in (v_r, v_only, v_s):
+        assert np.array_equal(v.view(np.int64), v_p.view(np.int64))
+    for gg in (g_r, g_s):
+        assert np.array_equal(gg.view(np.int64), g_p.view(np.int64))
+    assert rel_err(v_r, o.eval_jac_g(x)) <= RTOL
+    assert rel_err(g_r, o.eval_g(x)) <= RTOL
+    # a batch of instances through the row-parallel kernel (CTAs straddle instances)
+    g.set_option("unroll_colours", -1)
+    g.set_option("sweep_mode", 0)
+    rng = np.random.Generator(np.random.PCG64(22))
+    X = x[None, :] + 1e-2 * rng.uniform(-1, 1, (5, x.size))
+    GB, VB = g.eval_g_jac_batch(X)
+    for b in range(5):
+        g1, v1 = g.eval_g_jac(X[b])
+        assert np.array_equal(GB[b], g1) and np.array_equal(VB[b], v1)
+    g.set_option("unroll_colours", 0)
+    GP, VP = g.eval_g_jac_batch(X)
+    assert np.array_equal(VB.view(np.int64), VP.view(np.int64)) and np.array_equal(GB.view(np.int64), GP.view(np.int64))
+    g.close()
 
 
 @pytest.mark.parametrize("name,nb", [("quadrotor/u8x8", 64), ("cartpole/u8x8", 128), ("cartpole/u4x8", 64), ("brachistochrone/u2x8", 32)])
