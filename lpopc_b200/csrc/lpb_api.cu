@@ -414,6 +414,23 @@ struct lpb_handle {
     // What was written is remembered as (array, batch size, plan version); two sentinel values per instance (first
     // constant-tail value, first value of the first fill run) are re-read on every call and any mismatch -- a new
     // or overwritten array -- falls back to the full fill.
+    // ---- single-problem fast path (lpb_eval_f / grad_f / g / jac_g / h with host pointers) ----
+    // IPOPT asks for f, grad f, g and the Jacobian of the SAME x in four callbacks (LpopcIpopt.cpp:106-181); each used
+    // to cost an upload of x, a launch, a download and a synchronisation.  For small problems the first callback on a
+    // new x now runs ONE captured CUDA graph -- H2D of x from a pinned stage, objective + gradient + constraint /
+    // Jacobian kernels, one D2H of [f | grad | g | values] into a pinned stage -- and the other callbacks on that x
+    // are served from the stage (x is compared with the staged copy, which is IPOPT's new_x flag recomputed).
+    // eval_h adds one graph (lambda, sigma up; values down).  Option "fast_path": -1 auto (n + m + nnz_jac <= 262144),
+    // 0 off, 1 on.
+    struct FastPath {
+        int mode = -1;
+        bool built = false, x_valid = false;
+        cudaStream_t stream = nullptr;
+        double *h_in = nullptr, *h_out = nullptr, *h_hess = nullptr; // pinned stages
+        DevBuf<double> d_in, d_out, d_hess, d_scratch;
+        cudaGraphExec_t g_fgj = nullptr, g_h = nullptr;
+        long long hits = 0, evals = 0, launches_fgj = 0, launches_h = 0;
+    } fp;
     int persistent_values = 0;
     const double* filled_values = nullptr;
     int filled_nbatch = 0;
@@ -425,6 +442,10 @@ struct lpb_handle {
         for (auto* v : {&timed_cons, &timed_hess})
             for (auto& pr : *v) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
         if (own_stream && stream) cudaStreamDestroy(stream);
+        if (fp.g_fgj) cudaGraphExecDestroy(fp.g_fgj);
+        if (fp.g_h) cudaGraphExecDestroy(fp.g_h);
+        if (fp.stream) cudaStreamDestroy(fp.stream);
+        for (double* q : {fp.h_in, fp.h_out, fp.h_hess}) if (q) cudaFreeHost(q);
         for (cudaStream_t p : pipe) if (p) cudaStreamDestroy(p);
         if (h_seg_flags) cudaFreeHost(h_seg_flags);
         for (auto& hb : host_bufs)
@@ -486,6 +507,10 @@ static int run_compaction(lpb_handle* h, PhaseHost& p, int mode, int* out_a, int
 }
 
 // GetSizes -> GetBounds -> GetGuess(PS fill) -> RefreshSparsity of one mesh (LpLpopcAlgorithm.cpp:36-45)
+extern "C" {
+static void fast_path_drop(lpb_handle* h);
+}
+
 static void refresh(lpb_handle* h)
 {
     const int P = (int)h->ph.size(), Lp = (int)h->lk.size();
@@ -615,6 +640,7 @@ static void refresh(lpb_handle* h)
     CK(cudaStreamSynchronize(h->stream));
     h->fresh = true;
     h->err_fresh = false;
+    fast_path_drop(h);
 }
 
 // after the set of on-segments changed: device copy of the mask and the host's fill plan
@@ -935,6 +961,110 @@ int lpb_structure_dev(lpb_handle* h, const int** d_jac_iRow, const int** d_jac_j
     LPB_API_END(h)
 }
 
+// ---- single-problem fast path: captured graphs + pinned stages (see lpb_handle::FastPath) --------
+static bool fast_path_on(lpb_handle* h)
+{
+    if (h->fp.mode == 0) return false;
+    if (h->fp.mode > 0) return true;
+    return (long long)h->pd.n + h->pd.m + h->pd.nnz_jac <= 262144;
+}
+
+static void fast_path_drop(lpb_handle* h) // after a mesh change: graphs hold the old ProblemDev by value
+{
+    lpb_handle::FastPath& f = h->fp;
+    if (f.g_fgj) { cudaGraphExecDestroy(f.g_fgj); f.g_fgj = nullptr; }
+    if (f.g_h) { cudaGraphExecDestroy(f.g_h); f.g_h = nullptr; }
+    f.built = false;
+    f.x_valid = false;
+}
+
+static void fast_path_build(lpb_handle* h)
+{
+    lpb_handle::FastPath& f = h->fp;
+    const size_t n = (size_t)h->pd.n, m = (size_t)h->pd.m, nnz = (size_t)h->pd.nnz_jac, nnzh = (size_t)h->pd.nnz_h;
+    if (!f.stream) CK(cudaStreamCreateWithFlags(&f.stream, cudaStreamNonBlocking));
+    for (double** q : {&f.h_in, &f.h_out, &f.h_hess}) if (*q) { cudaFreeHost(*q); *q = nullptr; }
+    CK(cudaMallocHost((void**)&f.h_in, (n + m + 1) * sizeof(double)));
+    CK(cudaMallocHost((void**)&f.h_out, (1 + n + m + nnz) * sizeof(double)));
+    CK(cudaMallocHost((void**)&f.h_hess, (nnzh + 1) * sizeof(double)));
+    f.d_in.reserve(n + m + 1);
+    f.d_out.reserve(1 + n + m + nnz);
+    f.d_hess.reserve(nnzh + 1);
+    f.d_scratch.reserve(h->vt->scratch_doubles(h->pd, 1));
+    LaunchOpts o = h->opts;
+    o.ev_begin = o.ev_end = nullptr;
+    double* d_x = f.d_in.p;
+    double* d_lam = f.d_in.p + n;
+    double* d_sig = f.d_in.p + n + m;
+    double* d_f = f.d_out.p;
+    double* d_grad = f.d_out.p + 1;
+    double* d_g = f.d_out.p + 1 + n;
+    double* d_v = f.d_out.p + 1 + n + m;
+    cudaGraph_t graph = nullptr;
+    // graph 1: x up, every first-order callback, results down
+    CK(cudaStreamBeginCapture(f.stream, cudaStreamCaptureModeThreadLocal));
+    int l1 = 0, l2 = 0;
+    try {
+        CK(cudaMemcpyAsync(d_x, f.h_in, n * sizeof(double), cudaMemcpyHostToDevice, f.stream));
+        int rc = h->vt->objective(h->pd, h->consts.data(), f.stream, o, 1, d_x, d_f, f.d_scratch.p);
+        if (rc < 0) throw CudaError("fast path: objective launch failed during capture");
+        l1 += rc;
+        rc = h->vt->gradient(h->pd, h->consts.data(), f.stream, o, 1, d_x, d_grad, f.d_scratch.p);
+        if (rc < 0) throw CudaError("fast path: gradient launch failed during capture");
+        l1 += rc;
+        rc = h->vt->cons_jac(h->pd, h->consts.data(), f.stream, o, 1, d_x, d_g, d_v);
+        if (rc < 0) throw CudaError("fast path: constraint launch failed during capture");
+        l1 += rc;
+        CK(cudaMemcpyAsync(f.h_out, f.d_out.p, (1 + n + m + nnz) * sizeof(double), cudaMemcpyDeviceToHost, f.stream));
+    } catch (...) {
+        cudaStreamEndCapture(f.stream, &graph);
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        throw;
+    }
+    CK(cudaStreamEndCapture(f.stream, &graph));
+    CK(cudaGraphInstantiate(&f.g_fgj, graph, 0));
+    cudaGraphDestroy(graph);
+    // graph 2: multipliers up, Hessian values down (x is already on the device)
+    graph = nullptr;
+    CK(cudaStreamBeginCapture(f.stream, cudaStreamCaptureModeThreadLocal));
+    try {
+        CK(cudaMemcpyAsync(d_lam, f.h_in + n, (m + 1) * sizeof(double), cudaMemcpyHostToDevice, f.stream));
+        const int rc = h->vt->hessian(h->pd, h->consts.data(), f.stream, o, 1, d_x, d_sig, d_lam, f.d_hess.p, f.d_scratch.p);
+        if (rc < 0) throw CudaError("fast path: Hessian launch failed during capture");
+        l2 += rc;
+        CK(cudaMemcpyAsync(f.h_hess, f.d_hess.p, nnzh * sizeof(double), cudaMemcpyDeviceToHost, f.stream));
+    } catch (...) {
+        cudaStreamEndCapture(f.stream, &graph);
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        throw;
+    }
+    CK(cudaStreamEndCapture(f.stream, &graph));
+    CK(cudaGraphInstantiate(&f.g_h, graph, 0));
+    cudaGraphDestroy(graph);
+    f.launches_fgj = l1;
+    f.launches_h = l2;
+    f.built = true;
+    f.x_valid = false;
+}
+
+// makes the stage hold f, grad f, g and the Jacobian values of x (one graph launch when x is new)
+static void fast_path_first_order(lpb_handle* h, const double* x)
+{
+    lpb_handle::FastPath& f = h->fp;
+    if (!f.built) fast_path_build(h);
+    const size_t n = (size_t)h->pd.n;
+    if (f.x_valid && std::memcmp(f.h_in, x, n * sizeof(double)) == 0) { ++f.hits; return; }
+    std::memcpy(f.h_in, x, n * sizeof(double));
+    f.x_valid = false;
+    CK(cudaGraphLaunch(f.g_fgj, f.stream));
+    CK(cudaStreamSynchronize(f.stream));
+    h->launches += f.launches_fgj;
+    ++f.evals;
+    f.x_valid = true;
+}
+
 // ---- host-pointer entry points (TNLP-style) ---------------------------------------------------
 // option "auto_pin": see lpb_handle::auto_pin
 static void maybe_pin(lpb_handle* h, const void* p, size_t bytes)
@@ -1201,13 +1331,54 @@ int lpb_eval_h_batch(lpb_handle* h, int nbatch, const double* x, const double* o
     LPB_API_END(h)
 }
 
-int lpb_eval_f(lpb_handle* h, const double* x, double* obj_value) { return lpb_eval_f_batch(h, 1, x, obj_value); }
-int lpb_eval_grad_f(lpb_handle* h, const double* x, double* grad_f) { return lpb_eval_grad_f_batch(h, 1, x, grad_f); }
-int lpb_eval_g(lpb_handle* h, const double* x, double* g) { return lpb_eval_g_jac_batch(h, 1, x, g, nullptr); }
-int lpb_eval_g_jac(lpb_handle* h, const double* x, double* g, double* values) { return lpb_eval_g_jac_batch(h, 1, x, g, values); }
+// single-problem callbacks: served by the fast path when it is on (every one of f, grad f, g, values of the same x
+// from ONE graph launch), by the batch entry points otherwise
+static int fast_first_order(lpb_handle* h, const double* x, double* obj_value, double* grad_f, double* g, double* values)
+{
+    LPB_API_BEGIN(h)
+    need_fresh(h);
+    if (!x) throw ApiError(LPB_ERR_INVALID, "x is null");
+    fast_path_first_order(h, x);
+    const size_t n = (size_t)h->pd.n, m = (size_t)h->pd.m, nnz = (size_t)h->pd.nnz_jac;
+    const double* o = h->fp.h_out;
+    if (obj_value) *obj_value = o[0];
+    if (grad_f) std::memcpy(grad_f, o + 1, n * sizeof(double));
+    if (g) std::memcpy(g, o + 1 + n, m * sizeof(double));
+    if (values) std::memcpy(values, o + 1 + n + m, nnz * sizeof(double));
+    LPB_API_END(h)
+}
+
+static bool use_fast(lpb_handle* h)
+{
+    if (!h) return false;
+    try { need_fresh(h); } catch (...) { return false; } // the regular path reports the error
+    return fast_path_on(h);
+}
+
+int lpb_eval_f(lpb_handle* h, const double* x, double* obj_value)
+{
+    if (use_fast(h) && obj_value) return fast_first_order(h, x, obj_value, nullptr, nullptr, nullptr);
+    return lpb_eval_f_batch(h, 1, x, obj_value);
+}
+int lpb_eval_grad_f(lpb_handle* h, const double* x, double* grad_f)
+{
+    if (use_fast(h) && grad_f) return fast_first_order(h, x, nullptr, grad_f, nullptr, nullptr);
+    return lpb_eval_grad_f_batch(h, 1, x, grad_f);
+}
+int lpb_eval_g(lpb_handle* h, const double* x, double* g)
+{
+    if (use_fast(h) && g) return fast_first_order(h, x, nullptr, nullptr, g, nullptr);
+    return lpb_eval_g_jac_batch(h, 1, x, g, nullptr);
+}
+int lpb_eval_g_jac(lpb_handle* h, const double* x, double* g, double* values)
+{
+    if (use_fast(h)) return fast_first_order(h, x, nullptr, nullptr, g, values);
+    return lpb_eval_g_jac_batch(h, 1, x, g, values);
+}
 
 int lpb_eval_jac_g(lpb_handle* h, const double* x, int* iRow, int* jCol, double* values)
 {
+    if (values && use_fast(h)) return fast_first_order(h, x, nullptr, nullptr, nullptr, values);
     if (values) return lpb_eval_g_jac_batch(h, 1, x, nullptr, values);
     LPB_API_BEGIN(h)
     need_fresh(h);
@@ -1220,6 +1391,20 @@ int lpb_eval_jac_g(lpb_handle* h, const double* x, int* iRow, int* jCol, double*
 
 int lpb_eval_h(lpb_handle* h, const double* x, double obj_factor, const double* lambda, int* iRow, int* jCol, double* values)
 {
+    if (values && use_fast(h)) {
+        LPB_API_BEGIN(h)
+        if (!x || !lambda) throw ApiError(LPB_ERR_INVALID, "bad argument");
+        fast_path_first_order(h, x); // x on the device (no-op when IPOPT evaluated this x already)
+        lpb_handle::FastPath& f = h->fp;
+        const size_t n = (size_t)h->pd.n, m = (size_t)h->pd.m;
+        std::memcpy(f.h_in + n, lambda, m * sizeof(double));
+        f.h_in[n + m] = obj_factor;
+        CK(cudaGraphLaunch(f.g_h, f.stream));
+        CK(cudaStreamSynchronize(f.stream));
+        h->launches += f.launches_h;
+        std::memcpy(values, f.h_hess, (size_t)h->pd.nnz_h * sizeof(double));
+        LPB_API_END(h)
+    }
     if (values) return lpb_eval_h_batch(h, 1, x, &obj_factor, lambda, values);
     LPB_API_BEGIN(h)
     need_fresh(h);
@@ -1447,12 +1632,14 @@ int lpb_set_option_int(lpb_handle* h, const char* name, int value)
 {
     LPB_API_BEGIN(h)
     if (!name) throw ApiError(LPB_ERR_INVALID, "option name is null");
+    fast_path_drop(h); // kernel variants are baked into the captured graphs
     if (!std::strcmp(name, "colour_split")) h->opts.colour_split = value;
     else if (!std::strcmp(name, "pair_split")) h->opts.pair_split = value;
     else if (!std::strcmp(name, "block")) h->opts.block = value;
     else if (!std::strcmp(name, "host_fill_const")) h->host_fill_const = value;
     else if (!std::strcmp(name, "host_threads")) h->host_threads = value;
     else if (!std::strcmp(name, "sparse_return")) h->sparse_return = value;
+    else if (!std::strcmp(name, "fast_path")) { h->fp.mode = value; h->fp.x_valid = false; }
     else if (!std::strcmp(name, "persistent_values")) { h->persistent_values = value; h->filled_values = nullptr; }
     else if (!std::strcmp(name, "debug_skip")) h->debug_skip = value;
     else if (!std::strcmp(name, "auto_pin")) {
@@ -1506,6 +1693,8 @@ int lpb_get_stat(lpb_handle* h, const char* name, long long* value)
     else if (!std::strcmp(name, "sparse_on_doubles")) *value = h->seg_mask_init ? (long long)h->on_doubles : -1;
     else if (!std::strcmp(name, "head_doubles")) *value = (long long)h->pd.lin_val0;
     else if (!std::strcmp(name, "persistent_hits")) *value = h->persistent_hits;
+    else if (!std::strcmp(name, "fast_path_hits")) *value = h->fp.hits;
+    else if (!std::strcmp(name, "fast_path_evals")) *value = h->fp.evals;
     else if (!std::strncmp(name, "hess_I0.", 8) || !std::strncmp(name, "hess_E0.", 8) || !std::strncmp(name, "hess_L0.", 8)) {
         // first Hessian value of the I-part / E-part of phase <p>, of the link part of pair <q> (parity reports by segment)
         need_fresh(h);

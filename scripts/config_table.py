@@ -111,6 +111,35 @@ def main():
             print("%-26s %9s %9s %10s | %-8s %10.4f %10.3f %10.3f %10s" % (name if first else "", n if first else "", m if first else "", nnz if first else "",
                                                                     cb, d, h, hp, ("%.2f%s" % (r, "*" if port else "")) if r is not None else "-"), flush=True)
             first = False
+        if nb == 1 and n + m + nnz <= 262144:
+            # what a host IPOPT iteration costs: eval_f, eval_grad_f, eval_g, eval_jac_g (and eval_h) of ONE new x
+            # through the single-problem TNLP entry points -- with the fast path (one captured graph per new x, the other
+            # callbacks served from the pinned stage) and without (every callback uploads x, launches, downloads, syncs)
+            xs = [X[0] + 1e-6 * k for k in range(64)]
+            def four(k):
+                xx = xs[k % 64]
+                g.eval_f(xx); g.eval_grad_f(xx); g.eval_g(xx); g.eval_jac_g(xx)
+            def five(k):
+                four(k); g.eval_h(xs[k % 64], sigma, lam)
+            res = {}
+            for mode in (1, 0):
+                g.set_option("fast_path", mode)
+                for fn, key in ((four, "4"), (five, "5")):
+                    for k in range(4):
+                        fn(k)
+                    t0 = time.perf_counter()
+                    for k in range(4, 44):
+                        fn(k)
+                    res[(mode, key)] = 1e3 * (time.perf_counter() - t0) / 40
+            g.set_option("fast_path", -1)
+            rr = ""
+            if ref is not None:
+                t0 = time.perf_counter()
+                for k in range(3):
+                    ref.eval_f(xs[k]); ref.eval_grad_f(xs[k]); ref.eval_g(xs[k]); ref.eval_jac_g(xs[k])
+                rr = ", ref cpu %.3f ms" % (1e3 * (time.perf_counter() - t0) / 3)
+            print("%-26s %9s %9s %10s | one new x, f + grad_f + g + jac_g through the TNLP calls: fast path %.3f ms, without %.3f ms%s; "
+                  "with eval_h: %.3f ms vs %.3f ms" % ("", "", "", "", res[(1, "4")], res[(0, "4")], rr, res[(1, "5")], res[(0, "5")]), flush=True)
         if nb == 1:
             # per-mesh and per-solve steps around the callbacks (host wall clock, one problem): index maps + tables
             # rebuilt on the GPU, NLP -> optimal-control conversion, mesh-error estimate
