@@ -132,10 +132,13 @@ int lpb_probe_dependencies(lpb_handle* h, const double* x_guess, int* dep_out);
 int lpb_mesh_error(lpb_handle* h, const double* x, int* rows_out, double* rel_err, double* interval_max);
 /* Replaces: PhMeshRefineAlg::RefineMesh / ModifySegment (LpPhMeshRefineAlg.cpp:12-99; options
  * "desired-relative-error", "Nmax", "Nmin" of LpMeshRefiner.h:67-80).  Returns the refined mesh of every phase:
- * K_out[p], then K+1 mesh points and K node counts per phase appended to mesh_out / nodes_out (worst case
- * per interval: ceil((N_k + log(e/tol)/log(N_k)) / Nmin) sub-intervals).  Pass it to lpb_set_mesh. */
+ * K_out[p], then K+1 mesh points and K node counts per phase appended to mesh_out / nodes_out, whose capacities
+ * (in elements) are mesh_cap / nodes_cap.  The number of sub-intervals grows with the error (ceil((N_k +
+ * log(e/tol)/log(N_k)) / Nmin) per interval), so a call whose result does not fit fails with LPB_ERR_INVALID after
+ * filling K_out: size the arrays as sum(K) + nphases and sum(K) and call again.  A non-finite error estimate
+ * (diverged solution) is rejected.  Pass the result to lpb_set_mesh. */
 int lpb_refine_mesh_ph(lpb_handle* h, const double* x, double tol, int Nmax, int Nmin, int* no_more_refine,
-                       int* K_out, double* mesh_out, int* nodes_out);
+                       int* K_out, double* mesh_out, int mesh_cap, int* nodes_out, int nodes_cap);
 
 /* ---- NLP solution -> optimal-control solution (the step right after the solve) ----
  * Replaces: Nlp2OpConverter::Nlp2OpControl (Nlp2OPConverter.cpp:13-196).  From the NLP solution x and the

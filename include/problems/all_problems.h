@@ -12,6 +12,7 @@
 #include "quadrotor.h"
 #include "cartpole.h"
 #include "synthetic20.h"
+#include "two_stage.h"
 
 #define LPB_FOR_EACH_PROBLEM(X) \
     X(LpbHypersensitive)        \
@@ -21,5 +22,6 @@
     X(LpbBrachistochrone)       \
     X(LpbQuadrotor)             \
     X(LpbCartpole)              \
-    X(LpbSynthetic20)
+    X(LpbSynthetic20)           \
+    X(LpbTwoStage)
 #endif

@@ -37,7 +37,8 @@
     X(LpbBrachistochrone)\
     X(LpbQuadrotor)      \
     X(LpbCartpole)       \
-    X(LpbSynthetic20)
+    X(LpbSynthetic20)    \
+    X(LpbTwoStage)
 #define LPB_DECL(T) extern "C" const lpb::FunctorVTable* lpb_vtable_##T();
 LPB_REGISTRY(LPB_DECL)
 #undef LPB_DECL
@@ -1512,8 +1513,31 @@ int lpb_mesh_error(lpb_handle* h, const double* x, int* rows_out, double* rel_er
     LPB_API_END(h)
 }
 
+// hands the refined meshes to the caller: K_out always receives the interval counts, the arrays only when they fit
+static void emit_meshes(const std::vector<std::vector<double>>& meshes, const std::vector<std::vector<int>>& nodes, int* K_out,
+                        double* mesh_out, int mesh_cap, int* nodes_out, int nodes_cap)
+{
+    size_t km = 0, kn = 0;
+    for (size_t ip = 0; ip < meshes.size(); ++ip) {
+        K_out[ip] = (int)nodes[ip].size();
+        km += meshes[ip].size();
+        kn += nodes[ip].size();
+    }
+    if (km > (size_t)(mesh_cap > 0 ? mesh_cap : 0) || kn > (size_t)(nodes_cap > 0 ? nodes_cap : 0))
+        throw ApiError(LPB_ERR_INVALID, fmt("refined mesh needs %zu mesh points and %zu node counts, the caller's arrays hold %d and %d "
+                                            "(K_out has the interval counts: size the arrays as sum(K) + phases and sum(K), and call again)",
+                                            km, kn, mesh_cap, nodes_cap));
+    km = kn = 0;
+    for (size_t ip = 0; ip < meshes.size(); ++ip) {
+        std::memcpy(mesh_out + km, meshes[ip].data(), meshes[ip].size() * sizeof(double));
+        std::memcpy(nodes_out + kn, nodes[ip].data(), nodes[ip].size() * sizeof(int));
+        km += meshes[ip].size();
+        kn += nodes[ip].size();
+    }
+}
+
 int lpb_refine_mesh_ph(lpb_handle* h, const double* x, double tol, int Nmax, int Nmin, int* no_more_refine,
-                       int* K_out, double* mesh_out, int* nodes_out)
+                       int* K_out, double* mesh_out, int mesh_cap, int* nodes_out, int nodes_cap)
 {
     LPB_API_BEGIN(h)
     if (!no_more_refine || !K_out || !mesh_out || !nodes_out) throw ApiError(LPB_ERR_INVALID, "null output");
@@ -1521,13 +1545,18 @@ int lpb_refine_mesh_ph(lpb_handle* h, const double* x, double tol, int Nmax, int
     std::vector<std::vector<double>> rel, imax;
     mesh_error_eval(h, x, rel, imax);
     bool done = true;
-    size_t km = 0, kn = 0;
+    std::vector<std::vector<double>> meshes(h->ph.size());
+    std::vector<std::vector<int>> counts(h->ph.size());
     for (size_t ip = 0; ip < h->ph.size(); ++ip) {
         const PhaseHost& p = h->ph[ip];
-        std::vector<double> nm{-1.0};
-        std::vector<int> nn;
+        std::vector<double>& nm = meshes[ip];
+        std::vector<int>& nn = counts[ip];
+        nm.push_back(-1.0);
         for (size_t k = 0; k < p.nodes.size(); ++k) {
             const double m0 = p.mesh[k], mf = p.mesh[k + 1], emax = imax[ip][k];
+            // a diverged solution (inf / NaN error) has no meaningful refinement: the reference would cast a
+            // non-finite double to int here (undefined behaviour)
+            if (!std::isfinite(emax)) throw ApiError(LPB_ERR_INVALID, fmt("mesh error of phase %zu, interval %zu is not finite", ip + 1, k + 1));
             if (emax <= tol) { // LpPhMeshRefineAlg.cpp:37-47
                 nm.push_back(mf);
                 nn.push_back(p.nodes[k]);
@@ -1550,13 +1579,9 @@ int lpb_refine_mesh_ph(lpb_handle* h, const double* x, double tol, int Nmax, int
                 for (int i = 0; i < Bq; ++i) nn.push_back(Nmin);
             }
         }
-        K_out[ip] = (int)nn.size();
-        std::memcpy(mesh_out + km, nm.data(), nm.size() * sizeof(double));
-        std::memcpy(nodes_out + kn, nn.data(), nn.size() * sizeof(int));
-        km += nm.size();
-        kn += nn.size();
     }
     *no_more_refine = done ? 1 : 0;
+    emit_meshes(meshes, counts, K_out, mesh_out, mesh_cap, nodes_out, nodes_cap);
     LPB_API_END(h)
 }
 

@@ -741,6 +741,7 @@ size_t scratch_doubles(const ProblemDev& pd, int nbatch)
 template <class P>
 const FunctorVTable* make_vtable()
 {
+    static_assert(FunctorConcept<P>::value, "functor set does not satisfy include/lpb_functor.h");
     static const FunctorVTable vt = {
         P::name(), P::NS, P::NC, P::NPATH, P::NE_MAX, P::NL_MAX,
         (int)(sizeof(typename P::Consts) / sizeof(double)), P::HAS_ANALYTIC ? 1 : 0,

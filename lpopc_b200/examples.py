@@ -302,3 +302,33 @@ BUILDERS = {
     "orbit_raising": orbit_raising, "brachistochrone": brachistochrone, "quadrotor": quadrotor,
     "cartpole": cartpole, "synthetic20": synthetic20,
 }
+
+
+def two_stage(intervals=2, nodes=6, first_derive="analytic"):
+    """Two-stage transfer with an impulsive stage change (include/problems/two_stage.h): 2 phases, ns=2, nc=1, events in
+    both phases, one link pair with 2 links, user-supplied first derivatives of everything (first-derive = analytic
+    forwards DerivEvent / DerivLink / DerivMayer to the user, LpAnalyticDerive.hpp:18-47)."""
+    op = OptimalProblem(2, 1, "two_stage", [1.3, 0.05, 0.12, 4.0, 0.9, 0.05], first_derive=first_derive)
+    for ip in (1, 2):
+        ph = Phase(ip, 2, 1, 0, 0, 2 if ip == 1 else 1)
+        t0, t1 = (0.0, 1.0) if ip == 1 else (1.0, 2.5)
+        ph.SetTimeMin(t0, t1 - 0.2); ph.SetTimeMax(t0, t1 + 0.2)
+        ph.SetStateMin(-5, -5, -5); ph.SetStateMax(5, 5, 5)
+        ph.SetStateMin(-5, -5, -5); ph.SetStateMax(5, 5, 5)
+        ph.SetcontrolMin(-3); ph.SetcontrolMax(3)
+        if ip == 1:
+            for v in (0.2, 0.0):
+                ph.SeteventMin(v); ph.SeteventMax(v)
+        else:
+            ph.SeteventMin(0.9); ph.SeteventMax(1.1)
+        ph.SetTimeGuess(t0); ph.SetTimeGuess(t1)
+        ph.SetStateGuess(1, 0.2 if ip == 1 else 0.6); ph.SetStateGuess(1, 0.6 if ip == 1 else 1.0)
+        ph.SetStateGuess(2, 0.0 if ip == 1 else 0.5); ph.SetStateGuess(2, 0.6 if ip == 1 else 0.1)
+        ph.SetControlGuess(1, 0.5); ph.SetControlGuess(1, -0.2)
+        uniform_mesh(ph, intervals, nodes)
+        op.AddPhase(ph)
+    lk = Linkage(1, 1, 2)
+    for _ in range(2):
+        lk.SetLinkMin(0.0); lk.SetLinkMax(0.0)
+    op.AddLinkage(lk)
+    return op

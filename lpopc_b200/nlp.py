@@ -41,7 +41,7 @@ SIGNATURES = {
     "lpb_eval_g_jac": (C.c_int, [_vp, _dp, _dp, _dp]),
     "lpb_get_lgr_tables": (C.c_int, [_vp, C.c_int, _dp, _dp]),
     "lpb_mesh_error": (C.c_int, [_vp, _dp, _ip, _dp, _dp]),
-    "lpb_refine_mesh_ph": (C.c_int, [_vp, _dp, C.c_double, C.c_int, C.c_int, _ip, _ip, _dp, _ip]),
+    "lpb_refine_mesh_ph": (C.c_int, [_vp, _dp, C.c_double, C.c_int, C.c_int, _ip, _ip, _dp, C.c_int, _ip, C.c_int]),
     "lpb_probe_dependencies": (C.c_int, [_vp, _dp, _ip]),
     "lpb_eval_f_batch": (C.c_int, [_vp, C.c_int, _dp, _dp]),
     "lpb_eval_grad_f_batch": (C.c_int, [_vp, C.c_int, _dp, _dp]),
@@ -300,11 +300,17 @@ class TranscribedNLP:
         Defaults = the reference's "desired-relative-error", "Nmax", "Nmin" (LpMeshRefiner.h:67-80)."""
         x = _f64(x)
         P = len(self.op.phases)
-        worst = sum(sum(max(2, (n + 64) // nmin + 2) for n in p.nodesperinterval) for p in self.op.phases) + P
         K = np.zeros(P, dtype=np.int32)
-        mesh, nodes = np.empty(worst + P), np.zeros(worst, dtype=np.int32)
+        cap = sum(len(p.nodesperinterval) for p in self.op.phases) * 4 + P  # usually enough; the call reports what it needs
         done = C.c_int()
-        self._ck(self.lib.lpb_refine_mesh_ph(self.h, _d(x), float(tol), int(nmax), int(nmin), C.byref(done), _i(K), _d(mesh), _i(nodes)))
+        for attempt in range(2):
+            mesh, nodes = np.empty(cap + P), np.zeros(cap, dtype=np.int32)
+            rc = self.lib.lpb_refine_mesh_ph(self.h, _d(x), float(tol), int(nmax), int(nmin), C.byref(done), _i(K), _d(mesh), int(mesh.size),
+                                             _i(nodes), int(nodes.size))
+            if rc == 0 or attempt == 1 or int(K.sum()) <= cap:
+                self._ck(rc)
+                break
+            cap = int(K.sum())  # K_out holds the interval counts of the refined mesh: size exactly and call again
         out, km, kn = [], 0, 0
         for ip in range(P):
             out.append((mesh[km:km + K[ip] + 1].copy(), nodes[kn:kn + K[ip]].copy()))

@@ -80,8 +80,32 @@ public:
     void DerivDae(SolDae& s, Mat& deriv_state, Mat& deriv_path) override { DerivDaeImpl(s, deriv_state, deriv_path, std::integral_constant<bool, P::HAS_ANALYTIC>()); }
     void DerivLagrange(SolCost& s, Mat& d) override { DerivLagrangeImpl(s, d, std::integral_constant<bool, P::HAS_ANALYTIC>()); }
     void DerivMayer(SolCost& s, Vec& d) override { DerivMayerImpl(s, d, std::integral_constant<bool, P::HAS_ANALYTIC>()); }
+    // user derivatives of events and linkages (LpFunctionWrapper.h:64,67): deriv_event is ne x (2 ns + 2) with columns
+    // [x0 | t0 | xf | tf], derive_link is nl x 2 ns with columns [xf_left | x0_right]; the functor fills them row-major
+    void DerivEvent(SolEvent& s, Mat& d) override { DerivEventImpl(s, d, std::integral_constant<bool, P::HAS_ANALYTIC && (P::NE_MAX > 0)>()); }
+    void DerivLink(SolLink& s, Mat& d) override { DerivLinkImpl(s, d, std::integral_constant<bool, P::HAS_ANALYTIC && (P::NL_MAX > 0)>()); }
 
 private:
+    void DerivEventImpl(SolEvent&, Mat&, std::false_type) { throw LpoError("functor set has no analytic event derivatives"); }
+    void DerivLinkImpl(SolLink&, Mat&, std::false_type) { throw LpoError("functor set has no analytic linkage derivatives"); }
+    void DerivEventImpl(SolEvent& s, Mat& de, std::true_type)
+    {
+        const int ne = nevents_[s.phase_num_ - 1], W = 2 * NS + 2;
+        double d[NEa * (2 * NS + 2)];
+        P::devent(C, s.phase_num_, s.initial_time_, s.initial_state_.data(), s.terminal_time_, s.terminal_state_.data(), d);
+        de = Mat(ne, W, 0.0);
+        for (int q = 0; q < ne; ++q)
+            for (int c = 0; c < W; ++c) de(q, c) = d[q * W + c];
+    }
+    void DerivLinkImpl(SolLink& s, Mat& dl, std::true_type)
+    {
+        const int W = 2 * NS;
+        double d[NLa * 2 * NS];
+        P::dlink(C, s.left_state_.data(), s.right_state_.data(), d);
+        dl = Mat(nlinks_, W, 0.0);
+        for (int q = 0; q < nlinks_; ++q)
+            for (int c = 0; c < W; ++c) dl(q, c) = d[q * W + c];
+    }
     void DerivDaeImpl(SolDae&, Mat&, Mat&, std::false_type) { throw LpoError("functor set has no analytic derivatives"); }
     void DerivLagrangeImpl(SolCost&, Mat&, std::false_type) { throw LpoError("functor set has no analytic derivatives"); }
     void DerivMayerImpl(SolCost&, Vec&, std::false_type) { throw LpoError("functor set has no analytic derivatives"); }

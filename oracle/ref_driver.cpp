@@ -115,8 +115,31 @@ public:
     void DerivDae(SolDae& s, mat& deriv_state, mat& deriv_path) override { DerivDaeImpl(s, deriv_state, deriv_path, std::integral_constant<bool, P::HAS_ANALYTIC>()); }
     void DerivLagrange(SolCost& s, mat& d) override { DerivLagrangeImpl(s, d, std::integral_constant<bool, P::HAS_ANALYTIC>()); }
     void DerivMayer(SolCost& s, rowvec& d) override { DerivMayerImpl(s, d, std::integral_constant<bool, P::HAS_ANALYTIC>()); }
+    // user derivatives of events and linkages (LpFunctionWrapper.h:64,67; consumed at LpNLPWrapper.cpp:651-668, :441-519)
+    void DerivEvent(SolEvent& s, mat& d) override { DerivEventImpl(s, d, std::integral_constant<bool, P::HAS_ANALYTIC && (P::NE_MAX > 0)>()); }
+    void DerivLink(SolLink& s, mat& d) override { DerivLinkImpl(s, d, std::integral_constant<bool, P::HAS_ANALYTIC && (P::NL_MAX > 0)>()); }
 
 private:
+    void DerivEventImpl(SolEvent&, mat&, std::false_type) { throw RefError("functor set has no analytic event derivatives"); }
+    void DerivLinkImpl(SolLink&, mat&, std::false_type) { throw RefError("functor set has no analytic linkage derivatives"); }
+    void DerivEventImpl(SolEvent& s, mat& de, std::true_type)
+    {
+        const int ne = nevents_[s.phase_num_ - 1], W = 2 * NS + 2;
+        double d[NEa * (2 * NS + 2)];
+        P::devent(C, s.phase_num_, s.initial_time_, s.initial_state_.memptr(), s.terminal_time_, s.terminal_state_.memptr(), d);
+        de = zeros<mat>(ne, W);
+        for (int q = 0; q < ne; ++q)
+            for (int c = 0; c < W; ++c) de(q, c) = d[q * W + c];
+    }
+    void DerivLinkImpl(SolLink& s, mat& dl, std::true_type)
+    {
+        const int W = 2 * NS;
+        double d[NLa * 2 * NS];
+        P::dlink(C, s.left_state_.memptr(), s.right_state_.memptr(), d);
+        dl = zeros<mat>(nlinks_, W);
+        for (int q = 0; q < nlinks_; ++q)
+            for (int c = 0; c < W; ++c) dl(q, c) = d[q * W + c];
+    }
     void DerivDaeImpl(SolDae&, mat&, mat&, std::false_type) { throw RefError("functor set has no analytic derivatives"); }
     void DerivLagrangeImpl(SolCost&, mat&, std::false_type) { throw RefError("functor set has no analytic derivatives"); }
     void DerivMayerImpl(SolCost&, rowvec&, std::false_type) { throw RefError("functor set has no analytic derivatives"); }

@@ -33,6 +33,10 @@ def build(name):
         op = examples.cartpole(intervals=3, nodes=5)
     elif base == "synthetic20":
         op = examples.synthetic20(intervals=3, nodes=4)
+    elif base == "two_stage":
+        op = examples.two_stage()
+    elif base == "two_stage_fd":
+        op = examples.two_stage(first_derive="finite-difference")
     else:
         raise KeyError(name)
     if var == "ragged":
@@ -50,7 +54,7 @@ def build(name):
 
 CASES = ["hypersensitive", "hypersensitive/ragged", "hypersensitive/two", "hypersensitive_analytic", "bryson_denham",
          "bryson_denham/ragged", "launch", "launch/ragged", "orbit_raising", "brachistochrone", "quadrotor", "cartpole",
-         "synthetic20"]
+         "synthetic20", "two_stage", "two_stage/ragged", "two_stage_fd"]
 
 
 def lgr_points_of(oracle):
