@@ -139,6 +139,17 @@ int lpb_mesh_error(lpb_handle* h, const double* x, int* rows_out, double* rel_er
  * (diverged solution) is rejected.  Pass the result to lpb_set_mesh. */
 int lpb_refine_mesh_ph(lpb_handle* h, const double* x, double tol, int Nmax, int Nmin, int* no_more_refine,
                        int* K_out, double* mesh_out, int mesh_cap, int* nodes_out, int nodes_cap);
+/* Replaces: LiuHpMeshRefineAlg::RefineMesh (LpLiuHpMeshRefineAlg.cpp:12-260; "mesh-refine-methods" = "hp-Liu", options
+ * "desired-relative-error", "Nmax", "R" of LpMeshRefiner.h:54-61,67-80).  Per interval: keep / reduce the degree or merge
+ * with the neighbour where the error estimate meets tol, otherwise raise the degree where the solution is smooth (ratio
+ * of second derivatives against the previous grid <= ratio_R) and divide the interval where it is not.  The method
+ * compares with the previous grid, its error estimates and its solution: that history lives in the handle, the first
+ * call after lpb_create / lpb_refine_reset is "grid 0" (three more nodes where the error is too large), and the mesh
+ * passed to lpb_set_mesh between two calls must be the one the previous call returned.  Outputs and capacities as in
+ * lpb_refine_mesh_ph. */
+int lpb_refine_mesh_hp_liu(lpb_handle* h, const double* x, double tol, int Nmax, double ratio_R, int* no_more_refine,
+                           int* K_out, double* mesh_out, int mesh_cap, int* nodes_out, int nodes_cap);
+int lpb_refine_reset(lpb_handle* h); /* forget the hp-Liu history (a new solve sequence on this handle) */
 
 /* ---- NLP solution -> optimal-control solution (the step right after the solve) ----
  * Replaces: Nlp2OpConverter::Nlp2OpControl (Nlp2OPConverter.cpp:13-196).  From the NLP solution x and the

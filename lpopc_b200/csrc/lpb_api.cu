@@ -12,6 +12,7 @@
 #include "lpb_device.hpp"
 #include "lpb_structure.hpp"
 #include "lpb_tables.hpp"
+#include "lpb_refine_liu.hpp"
 #include "lpb_kernels.cuh"
 
 #include <cmath>
@@ -432,6 +433,7 @@ struct lpb_handle {
         cudaGraphExec_t g_fgj = nullptr, g_h = nullptr;
         long long hits = 0, evals = 0, launches_fgj = 0, launches_h = 0;
     } fp;
+    LiuRefiner liu; // history of the hp-Liu refinement (lpb_refine_mesh_hp_liu, lpb_refine_reset)
     int persistent_values = 0;
     const double* filled_values = nullptr;
     int filled_nbatch = 0;
@@ -1582,6 +1584,48 @@ int lpb_refine_mesh_ph(lpb_handle* h, const double* x, double tol, int Nmax, int
     }
     *no_more_refine = done ? 1 : 0;
     emit_meshes(meshes, counts, K_out, mesh_out, mesh_cap, nodes_out, nodes_cap);
+    LPB_API_END(h)
+}
+
+int lpb_refine_mesh_hp_liu(lpb_handle* h, const double* x, double tol, int Nmax, double ratio_R, int* no_more_refine,
+                           int* K_out, double* mesh_out, int mesh_cap, int* nodes_out, int nodes_cap)
+{
+    LPB_API_BEGIN(h)
+    if (!no_more_refine || !K_out || !mesh_out || !nodes_out) throw ApiError(LPB_ERR_INVALID, "null output");
+    if (!(tol > 0) || Nmax < 2 || !(ratio_R > 0)) throw ApiError(LPB_ERR_INVALID, "bad refinement options");
+    std::vector<std::vector<double>> rel, imax;
+    mesh_error_eval(h, x, rel, imax); // GPU: interpolation to one more LGR point per interval, dae there, integration defect
+    const int ns = h->vt->NS, nc = h->vt->NC;
+    std::vector<LiuPhaseInput> in(h->ph.size());
+    for (size_t ip = 0; ip < h->ph.size(); ++ip) {
+        const PhaseHost& p = h->ph[ip];
+        LiuPhaseInput& q = in[ip];
+        q.ns = ns;
+        q.mesh = p.mesh;
+        q.nodes = p.nodes;
+        q.tau = p.tab.tau;
+        q.rel = rel[ip];
+        for (double e : q.rel)
+            if (!std::isfinite(e)) throw ApiError(LPB_ERR_INVALID, fmt("mesh error of phase %zu is not finite", ip + 1));
+        const size_t N = (size_t)p.tab.N;
+        const double* xb = x + h->pd.ph[ip].var0;
+        q.state.assign(xb, xb + (size_t)ns * (N + 1)); // state j at j(N+1) + k: already (N+1) x ns column-major
+        (void)nc;
+    }
+    std::vector<std::vector<double>> meshes;
+    std::vector<std::vector<int>> counts;
+    LiuRefiner next = h->liu; // the history advances only when the caller received the result
+    const bool done = next.refine(in, tol, Nmax, ratio_R, meshes, counts);
+    *no_more_refine = done ? 1 : 0;
+    emit_meshes(meshes, counts, K_out, mesh_out, mesh_cap, nodes_out, nodes_cap);
+    h->liu = std::move(next);
+    LPB_API_END(h)
+}
+
+int lpb_refine_reset(lpb_handle* h)
+{
+    LPB_API_BEGIN(h)
+    h->liu.reset();
     LPB_API_END(h)
 }
 

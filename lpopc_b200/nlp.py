@@ -42,6 +42,8 @@ SIGNATURES = {
     "lpb_get_lgr_tables": (C.c_int, [_vp, C.c_int, _dp, _dp]),
     "lpb_mesh_error": (C.c_int, [_vp, _dp, _ip, _dp, _dp]),
     "lpb_refine_mesh_ph": (C.c_int, [_vp, _dp, C.c_double, C.c_int, C.c_int, _ip, _ip, _dp, C.c_int, _ip, C.c_int]),
+    "lpb_refine_mesh_hp_liu": (C.c_int, [_vp, _dp, C.c_double, C.c_int, C.c_double, _ip, _ip, _dp, C.c_int, _ip, C.c_int]),
+    "lpb_refine_reset": (C.c_int, [_vp]),
     "lpb_probe_dependencies": (C.c_int, [_vp, _dp, _ip]),
     "lpb_eval_f_batch": (C.c_int, [_vp, C.c_int, _dp, _dp]),
     "lpb_eval_grad_f_batch": (C.c_int, [_vp, C.c_int, _dp, _dp]),
@@ -166,6 +168,7 @@ class TranscribedNLP:
     def set_mesh(self, phase, meshpoints, nodes):
         mp, nd = _f64(meshpoints), np.ascontiguousarray(nodes, dtype=np.int32)
         self._ck(self.lib.lpb_set_mesh(self.h, phase, len(nd), _d(mp), _i(nd)))
+        self.op.phases[phase].set_mesh(mp, nd)  # the Python mirror sizes output arrays from it
 
     def refresh(self):
         self._ck(self.lib.lpb_refresh(self.h))
@@ -317,6 +320,33 @@ class TranscribedNLP:
             km += K[ip] + 1
             kn += K[ip]
         return bool(done.value), out
+
+    def refine_mesh_hp_liu(self, x, tol=1e-6, nmax=16, ratio_r=1.2):
+        """hp-Liu refinement decision (LiuHpMeshRefineAlg::RefineMesh): (no_more_refine, [(meshpoints, nodes) per phase]).
+        Stateful (history in the handle, refine_reset() starts over); defaults = the reference's options
+        "desired-relative-error", "Nmax", "R" (LpMeshRefiner.h:67-80)."""
+        x = _f64(x)
+        P = len(self.op.phases)
+        K = np.zeros(P, dtype=np.int32)
+        cap = sum(len(p.nodesperinterval) for p in self.op.phases) * 4 + P
+        done = C.c_int()
+        for attempt in range(2):  # a result that does not fit leaves the history untouched and reports the sizes in K
+            mesh, nodes = np.empty(cap + P), np.zeros(cap, dtype=np.int32)
+            rc = self.lib.lpb_refine_mesh_hp_liu(self.h, _d(x), float(tol), int(nmax), float(ratio_r), C.byref(done), _i(K), _d(mesh),
+                                                 int(mesh.size), _i(nodes), int(nodes.size))
+            if rc == 0 or attempt == 1 or int(K.sum()) <= cap:
+                self._ck(rc)
+                break
+            cap = int(K.sum())
+        out, km, kn = [], 0, 0
+        for ip in range(P):
+            out.append((mesh[km:km + K[ip] + 1].copy(), nodes[kn:kn + K[ip]].copy()))
+            km += K[ip] + 1
+            kn += K[ip]
+        return bool(done.value), out
+
+    def refine_reset(self):
+        self._ck(self.lib.lpb_refine_reset(self.h))
 
     def probe_dependencies(self, x_guess):
         x = _f64(x_guess)

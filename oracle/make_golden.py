@@ -83,5 +83,32 @@ def main():
         print("%-28s n=%-6d m=%-6d nnz_jac=%-7d nnz_h=%-7d %6.1f KB" % ((name,) + r.nlp_info() + (os.path.getsize(path) / 1024,)))
 
 
+def liu_sequences():
+    """hp-Liu refinement sequences of the reference (LiuHpMeshRefineAlg, stateful): LIU_STEPS consecutive decisions on a
+    manufactured solution re-sampled on every new mesh -> tests/golden/liu__<case>.npz."""
+    out = os.path.join(ROOT, "tests", "golden")
+    for name in cases.LIU_CASES:
+        op = cases.build(name)
+        r = RefOracle(op)
+        d = {}
+        for step in range(cases.LIU_STEPS):
+            pts = [r.tables(ip)["points"] for ip in range(len(op.phases))]
+            x = cases.manufactured_x(name, op, pts)
+            d["s%d_in_mesh" % step] = np.asarray(op.phases[0].meshpoints, dtype=np.float64)
+            d["s%d_in_nodes" % step] = np.asarray(op.phases[0].nodesperinterval, dtype=np.int32)
+            d["s%d_rel" % step] = r.mesh_error(x)[0]
+            done, meshes = r.refine_hp_liu(x, **cases.LIU_OPTIONS)
+            mp, nd = meshes[0]
+            d["s%d_done" % step] = np.array(int(done))
+            d["s%d_mesh" % step], d["s%d_nodes" % step] = mp, nd
+            print("%-24s step %d: %3d intervals, %4d nodes -> %3d intervals, %4d nodes%s" %
+                  (name, step, len(op.phases[0].nodesperinterval), int(np.sum(op.phases[0].nodesperinterval)), nd.size, int(nd.sum()), "  (done)" if done else ""))
+            op.phases[0].set_mesh(mp, nd)
+            r.set_mesh(0, mp, nd)
+            r.refresh()
+        np.savez_compressed(os.path.join(out, "liu__" + name.replace("/", "__") + ".npz"), **d)
+
+
 if __name__ == "__main__":
     main()
+    liu_sequences()

@@ -18,7 +18,7 @@ CXXFLAGS := -std=c++14 -O2 -w -fPIC -ffp-contract=off -include functional \
 REF_SRCS := SparseMatrix/LpSparseMatrix.cpp SparseMatrix/LpSparseArray.cpp \
             Core/RPMGenerator.cpp Core/LpSizeChecker.cpp Core/LpBoundsChecker.cpp Core/LpOptimalProblem.cpp \
             Core/LpGuessChecker.cpp Core/LpDerivDependciesChecker.cpp Core/LpFiniteDifferenceDerive.cpp \
-            Core/LpNLPWrapper.cpp Core/LpHessian.cpp Core/LpSacleOCP.cpp Core/LpSolutionError.cpp Core/LpPhMeshRefineAlg.cpp Core/Nlp2OPConverter.cpp \
+            Core/LpNLPWrapper.cpp Core/LpHessian.cpp Core/LpSacleOCP.cpp Core/LpSolutionError.cpp Core/LpPhMeshRefineAlg.cpp Core/LpLiuHpMeshRefineAlg.cpp Core/Nlp2OPConverter.cpp \
             Common/LpOption.cpp Common/LpOptionList.cpp Common/LpReporter.cpp Common/LpDebug.cpp Common/LpUtils.cpp
 # the reference's example programs: their user-function classes are the second opinion on include/problems/*.h.
 # -Dmain=...: each example's main() becomes an unused internal function (it needs IPOPT to link)

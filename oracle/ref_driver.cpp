@@ -26,6 +26,7 @@
 #include "LpNLPWrapper.hpp"
 #include "LpOptimalProblem.hpp"
 #include "LpPhMeshRefineAlg.hpp"
+#include "LpLiuHpMeshRefineAlg.hpp"
 #include "LpSizeChecker.h"
 #include "LpSolutionError.h"
 #include "Nlp2OPConverter.h"
@@ -213,6 +214,9 @@ struct Ref {
     shared_ptr<RPMGenerator> rpm;
     shared_ptr<NLPWrapper> nlp;
     vec jI, jJ, hI, hJ;
+    // hp-Liu refinement object: it keeps the history of meshes / states across calls and a pointer to the
+    // LpCalculateData it was built with, so `cd` is kept (not re-created) from its construction on
+    shared_ptr<LiuHpMeshRefineAlg> liu;
 };
 
 template <class P>
@@ -289,7 +293,7 @@ void refresh(Ref& r)
         for (double v : r.lk[l].lmax) lk->SetLinkMax(v);
         r.op->AddLinkage(lk);
     }
-    r.cd.reset(new LpCalculateData());
+    if (!r.liu) r.cd.reset(new LpCalculateData()); // the reference keeps ONE LpCalculateData per problem across grids
     r.cd->autoscale = false;
     r.cd->current_grid = 1;
     // LpopcAlgorithm::Initialized (LpLpopcAlgorithm.cpp:157-246)
@@ -632,6 +636,47 @@ int lpo_refine_ph(void* h, const double* x, double tol, int Nmax, int Nmin, int*
             for (size_t i = 0; i < meshes[ip]->nodesPerInterval.n_elem; ++i) nodes_out[kn++] = (int)meshes[ip]->nodesPerInterval(i);
         }
         r->fresh = false; // RefineMesh rewrote the mesh inside r->op; the next call rebuilds from r->ph
+    })
+}
+
+// LiuHpMeshRefineAlg::RefineMesh (Core/LpLiuHpMeshRefineAlg.cpp:12-260) on the NLP solution x.  The algorithm object
+// persists in the handle (mesh / state / error history); lpo_refine_reset drops it.  Outputs as lpo_refine_ph.
+int lpo_refine_hp_liu(void* h, const double* x, double tol, int Nmax, double R, int* no_more_refine, int* K_out, double* mesh_out, int* nodes_out)
+{
+    Ref* r = (Ref*)h;
+    REF_GUARD(r, {
+        if (!r->fresh) refresh(*r);
+        ensure_logger();
+        if (!r->liu) {
+            shared_ptr<LpReporter> rep(new LpReporter());
+            r->liu.reset(new LiuHpMeshRefineAlg(Nmax, R, tol, r->fun, r->cd, rep));
+        }
+        fill_result(*r, x);
+        std::vector<shared_ptr<LpMesh>> meshes;
+        const bool done = r->liu->RefineMesh(r->op, meshes);
+        *no_more_refine = done ? 1 : 0;
+        size_t km = 0, kn = 0;
+        for (size_t ip = 0; ip < meshes.size(); ++ip) {
+            if (!meshes[ip]) { // phases the algorithm skipped keep their mesh (the reference leaves the entry empty)
+                K_out[ip] = (int)r->ph[ip].nodes.size();
+                for (double m : r->ph[ip].mesh) mesh_out[km++] = m;
+                for (int n : r->ph[ip].nodes) nodes_out[kn++] = n;
+                continue;
+            }
+            K_out[ip] = (int)meshes[ip]->nodesPerInterval.n_elem;
+            for (size_t i = 0; i < meshes[ip]->meshpoints.n_elem; ++i) mesh_out[km++] = meshes[ip]->meshpoints(i);
+            for (size_t i = 0; i < meshes[ip]->nodesPerInterval.n_elem; ++i) nodes_out[kn++] = (int)meshes[ip]->nodesPerInterval(i);
+        }
+        r->fresh = false; // RefineMesh rewrote the mesh inside r->op; the next call rebuilds from r->ph
+    })
+}
+
+int lpo_refine_reset(void* h)
+{
+    Ref* r = (Ref*)h;
+    REF_GUARD(r, {
+        r->liu.reset();
+        r->fresh = false;
     })
 }
 

@@ -70,3 +70,35 @@ def inputs(op, oracle, seed):
     lam = rng.uniform(-1, 1, oracle.m)
     sigma = float(rng.uniform(0.5, 1.5))
     return guess, x, sigma, lam
+
+
+# ---- manufactured solutions for the mesh-refinement sequences (hp-Liu goldens) ------------------------------------
+LIU_CASES = ["hypersensitive/u8x4", "bryson_denham/u7x6"]
+LIU_STEPS = 4
+LIU_OPTIONS = dict(tol=1e-5, nmax=12, ratio_r=1.2)
+
+
+def manufactured_x(name, op, points):
+    """An NLP vector whose states and controls satisfy the problem's dynamics exactly as functions of time, sampled on
+    the composite LGR points of the current mesh (points = [tau per phase]): the mesh-error estimate then measures
+    genuine interpolation error -- small where the trajectory is smooth, large in its boundary layers -- which is what
+    the refinement decisions react to.  hypersensitive: x(t) with two boundary layers, u = x' + x^3.  Bryson-Denham:
+    x1 = a sin(w t), x2 = x1', u = x1'', x3 = int u^2 / 2."""
+    base = name.split("/")[0]
+    tau = np.concatenate([np.asarray(points[0], dtype=np.float64), [1.0]])
+    N = tau.size - 1
+    if base == "hypersensitive":
+        t0, tf = 0.0, 5000.0
+        s = 9.0
+        x = 1.5 * np.exp(-(tau + 1.0) * s) + np.exp((tau - 1.0) * s) + 0.05 * np.sin(2.0 * tau)
+        dx_dtau = -1.5 * s * np.exp(-(tau + 1.0) * s) + s * np.exp((tau - 1.0) * s) + 0.1 * np.cos(2.0 * tau)
+        u = dx_dtau * (2.0 / (tf - t0)) + x ** 3
+        return np.concatenate([x, u[:N], [t0, tf]])
+    if base == "bryson_denham":
+        t0, tf = 0.0, 1.3
+        t = (tf - t0) * (tau + 1.0) / 2.0 + t0
+        a, w = 0.1, 6.0
+        x1, x2, u = a * np.sin(w * t), a * w * np.cos(w * t), -a * w * w * np.sin(w * t)
+        x3 = 0.5 * (a * w * w) ** 2 * (t / 2.0 - np.sin(2.0 * w * t) / (4.0 * w))
+        return np.concatenate([x1, x2, x3, u[:N], [t0, tf]])
+    raise KeyError(name)

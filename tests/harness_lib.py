@@ -15,13 +15,15 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        srcs = [os.path.join(HERE, "host_harness.cpp"), os.path.join(ROOT, "lpopc_b200", "csrc", "lpb_tables.cpp"),
-                os.path.join(ROOT, "lpopc_b200", "csrc", "lpb_structure.hpp"), os.path.join(ROOT, "lpopc_b200", "csrc", "lpb_tables.hpp")]
+        csrc = os.path.join(ROOT, "lpopc_b200", "csrc")
+        srcs = [os.path.join(HERE, "host_harness.cpp"), os.path.join(csrc, "lpb_tables.cpp"), os.path.join(csrc, "lpb_refine_liu.cpp"),
+                os.path.join(csrc, "lpb_structure.hpp"), os.path.join(csrc, "lpb_tables.hpp"), os.path.join(csrc, "lpb_refine_liu.hpp")]
         if not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in srcs):
-            subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-shared", "-o", LIB, srcs[0], srcs[1]],
+            subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-shared", "-o", LIB, srcs[0], srcs[1], srcs[2]],
                            check=True, capture_output=True)
         _lib = C.CDLL(LIB)
         _lib.lpbt_create.restype = C.c_void_p
+        _lib.lpbt_liu_create.restype = C.c_void_p
     return _lib
 
 
@@ -72,3 +74,30 @@ class Harness:
         fa, fb, fv = np.empty(nf, dtype=np.int32), np.empty(nf, dtype=np.int32), np.empty(nf)
         lib().lpbt_dfull(self.h, phase, fa.ctypes.data_as(_ip), fb.ctypes.data_as(_ip), fv.ctypes.data_as(_dp))
         return {"points": tau, "weights": w, "ddiag": dd, "Doffdiag": (a, b, v), "D": (fa, fb, fv)}
+
+
+class LiuHarness:
+    """The product's hp-Liu decision logic (lpopc_b200/csrc/lpb_refine_liu.cpp) on the CPU, fed with given error estimates."""
+
+    def __init__(self):
+        self.h = C.c_void_p(lib().lpbt_liu_create())
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().lpbt_liu_destroy(self.h)
+            self.h = None
+
+    def refine(self, ns, mesh, nodes, rel, state, tol, nmax, ratio_r):
+        mesh = np.ascontiguousarray(mesh, dtype=np.float64)
+        nodes = np.ascontiguousarray(nodes, dtype=np.int32)
+        rel = np.asfortranarray(rel, dtype=np.float64)      # rows x ns, column-major
+        state = np.asfortranarray(state, dtype=np.float64)  # (N + 1) x ns, column-major
+        cap = 64 * nodes.size + 1024
+        mo, no = np.empty(cap + 1), np.zeros(cap, dtype=np.int32)
+        done, K = C.c_int(), C.c_int()
+        rc = lib().lpbt_liu_refine(self.h, C.c_int(ns), C.c_int(nodes.size), mesh.ctypes.data_as(_dp), nodes.ctypes.data_as(_ip),
+                                   rel.ctypes.data_as(_dp), C.c_int(rel.shape[0]), state.ctypes.data_as(_dp), C.c_double(tol), C.c_int(nmax),
+                                   C.c_double(ratio_r), C.byref(done), C.byref(K), mo.ctypes.data_as(_dp), no.ctypes.data_as(_ip), C.c_int(cap))
+        if rc != 0:
+            raise RuntimeError("hp-Liu harness failed: %d" % rc)
+        return bool(done.value), mo[:K.value + 1].copy(), no[:K.value].copy()

@@ -8,6 +8,7 @@
 // and is never loaded by the product.
 #include "../lpopc_b200/csrc/lpb_structure.hpp"
 #include "../lpopc_b200/csrc/lpb_tables.hpp"
+#include "../lpopc_b200/csrc/lpb_refine_liu.hpp"
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -144,3 +145,34 @@ int lpbt_dfull(void* p, int phase, int* a, int* b, double* v)
 }
 
 } // extern "C"
+
+// ---- hp-Liu refinement decision (lpb_refine_liu.cpp) on given error estimates: single phase ----
+extern "C" {
+void* lpbt_liu_create() { return new lpb::LiuRefiner(); }
+void lpbt_liu_destroy(void* p) { delete static_cast<lpb::LiuRefiner*>(p); }
+int lpbt_liu_refine(void* p, int ns, int K, const double* mesh, const int* nodes, const double* rel, int rel_rows, const double* state,
+                    double tol, int Nmax, double R, int* done, int* K_out, double* mesh_out, int* nodes_out, int cap)
+{
+    try {
+        lpb::PhaseTables tab;
+        lpb::build_phase_tables(K, mesh, nodes, tab);
+        std::vector<lpb::LiuPhaseInput> in(1);
+        in[0].ns = ns;
+        in[0].mesh.assign(mesh, mesh + K + 1);
+        in[0].nodes.assign(nodes, nodes + K);
+        in[0].tau = tab.tau;
+        in[0].rel.assign(rel, rel + (size_t)rel_rows * ns);
+        in[0].state.assign(state, state + (size_t)(tab.N + 1) * ns);
+        std::vector<std::vector<double>> mo;
+        std::vector<std::vector<int>> no;
+        *done = static_cast<lpb::LiuRefiner*>(p)->refine(in, tol, Nmax, R, mo, no) ? 1 : 0;
+        if ((int)no[0].size() > cap) return -2;
+        *K_out = (int)no[0].size();
+        std::memcpy(mesh_out, mo[0].data(), mo[0].size() * sizeof(double));
+        std::memcpy(nodes_out, no[0].data(), no[0].size() * sizeof(int));
+        return 0;
+    } catch (const std::exception&) {
+        return -1;
+    }
+}
+}

@@ -270,6 +270,27 @@ class RefOracle(Oracle):
         return bool(done.value), out
 
 
+def _ref_refine_hp_liu(self, x, tol=1e-6, nmax=16, ratio_r=1.2):
+    """LiuHpMeshRefineAlg::RefineMesh of the reference (stateful: the algorithm object lives in the handle):
+    (no_more_refine, [(meshpoints, nodes) per phase])."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    P = len(self.op.phases)
+    worst = sum(len(p.nodesperinterval) for p in self.op.phases) * 64 + 4096
+    K = np.zeros(P, dtype=np.int32)
+    mesh, nodes = np.empty(worst + P), np.zeros(worst, dtype=np.int32)
+    done = C.c_int()
+    self._check(self.L.lpo_refine_hp_liu(self.h, _d(x), C.c_double(tol), C.c_int(nmax), C.c_double(ratio_r), C.byref(done), _i(K), _d(mesh), _i(nodes)))
+    out, km, kn = [], 0, 0
+    for ip in range(P):
+        out.append((mesh[km:km + K[ip] + 1].copy(), nodes[kn:kn + K[ip]].copy()))
+        km += K[ip] + 1
+        kn += K[ip]
+    return bool(done.value), out
+
+
+RefOracle.refine_hp_liu = _ref_refine_hp_liu
+
+
 def detmath(which, x):
     x = np.ascontiguousarray(x, dtype=np.float64)
     y = np.empty_like(x)
