@@ -173,7 +173,7 @@ class DenseKKT:
         ipm, J = self.ipm, self.J
         nf, me, rho = ipm.nf, ipm.me, ipm.rho
         dev = J.device
-        W = ipm._dense_hess(hv)
+        W = hv if hv.dim() == 3 else ipm._dense_hess(hv)  # [B, nf, nf]: a quasi-Newton matrix handed over as it is
         # factor H_rho = W + Sigma + rho J^T J + dw I.  Adding rho J^T (J dx + c) = 0 to the first
         # block row leaves (dx, dlam) unchanged, and by Debreu's lemma H_rho is positive definite for
         # large rho exactly when the Hessian is positive definite on the null space of J -- the
@@ -193,6 +193,7 @@ class DenseKKT:
             if not bool(bad.any()):
                 break
             dw = torch.where(bad, torch.where(dw == 0, torch.full_like(dw, 1e-4), dw * (100.0 if _try < 2 else 8.0)), dw)
+        not_pd = (info != 0) & (~done)  # still indefinite after the last try: the step of such an instance is not trusted (status 2)
         # condensed system of [H J^T; J 0][dx; dlam] = -[rhs1; c] with H = L L^T:
         #   Y = L^-1 J^T, y = L^-1 rhs1, S = Y^T Y, S dlam = c - Y^T y, dx = -L^-T (y + Y dlam)
         Yr = torch.linalg.solve_triangular(Lh, torch.cat([J.transpose(1, 2), rhs1.unsqueeze(2)], dim=2), upper=False)
@@ -207,6 +208,7 @@ class DenseKKT:
             S[:, dS, dS] += torch.where(bad_s, 1e-8, 0.0).unsqueeze(1)
             Ls, info_s = blocked_cholesky_ex(S)
             failed = (info_s != 0) & (~done)
+        failed = failed | not_pd
         rhs2 = c.unsqueeze(2) - torch.bmm(Y.transpose(1, 2), y)
         dlam = torch.cholesky_solve(rhs2, Ls)
         dx = -torch.linalg.solve_triangular(Lh.transpose(1, 2), y + torch.bmm(Y, dlam), upper=True).squeeze(2)
@@ -515,7 +517,7 @@ class BlockTridiagKKT:
             ddl = g * (self._Jmul(ddx) - res2)
             dxb = dxb + ddx
             dlb = dlb + ddl
-        failed = torch.zeros_like(done)
+        failed = (info != 0) & (~done)  # still indefinite after the last regularisation try: status 2, not a silent step
         return self.from_blocks(dxb), self.dual_from_blocks(dlb), dw, failed
 
 
@@ -543,7 +545,8 @@ def interval_blocks(op, n_total):
 class BatchedIPM:
     """Lockstep primal-dual interior-point method over a batch of instances of one NLP."""
 
-    def __init__(self, ev, tol=1e-6, max_iter=100, mu0=0.1, rho=1e3, verbose=False, var_blocks=None, kkt_gamma=1e6, kkt_refine=3, kkt_fused=True, compact_at=0.5):
+    def __init__(self, ev, tol=1e-6, max_iter=100, mu0=0.1, rho=1e3, verbose=False, var_blocks=None, kkt_gamma=1e6, kkt_refine=3, kkt_fused=True, compact_at=0.5,
+                 linesearch="filter", hessian="exact", lbfgs_memory=6):
         """var_blocks: optional block id (mesh interval) per NLP variable (`interval_blocks(op, n)`): selects the
         block-tridiagonal KKT step when the problem's coupling allows it, the dense condensed step otherwise."""
         self.var_blocks = var_blocks
@@ -556,6 +559,17 @@ class BatchedIPM:
             ev = SlackEvaluator(ev)  # inequality rows -> equalities with bounded slacks
         self.ev, self.tol, self.max_iter, self.mu0, self.rho, self.verbose = ev, tol, max_iter, mu0, rho, verbose
         self.n, self.m = ev.n, ev.m
+        # globalisation: "filter" = filter line search in the manner of IPOPT (Waechter & Biegler 2006, section 2.3:
+        # a trial point is acceptable when it improves the constraint violation OR the barrier objective enough and
+        # is not dominated by the filter; an Armijo condition on the objective when the switching condition holds),
+        # the reference's setting (IPOPT defaults, LpNLPSolver.cpp:27-33); "merit" = l1 exact penalty with Armijo
+        self.linesearch = linesearch
+        self.filter_slots = 24
+        # hessian = "exact": eval_h (the reference's "hessian-approximation" = "exact"); "limited-memory": damped
+        # L-BFGS on the Lagrangian gradient with `lbfgs_memory` pairs, IPOPT's default and the reference's
+        # (LpNLPSolver.cpp:30-33, LpNLPWrapper.hpp:69-76) -- no eval_h calls at all.  Dense KKT step only.
+        self.hessian = hessian
+        self.lbfgs_memory = lbfgs_memory
 
     # ---- problem structure shared by all instances ------------------------------------------------
     def _setup(self, xl, xu, gl, gu):
@@ -628,6 +642,56 @@ class BatchedIPM:
         H.index_add_(1, self.h_flat, vals[:, self.h_sel])
         return H.view(B, self.nf, self.nf)
 
+    # ---- limited-memory quasi-Newton Hessian of the Lagrangian ----------------------------------------
+    def _lbfgs_push(self, S, Y, cnt, sk, yk, active):
+        """Appends the pair (s, y) of every active instance (Powell-damped against B0 = delta I so that s'y > 0) and
+        drops the oldest when the memory is full."""
+        sy = (sk * yk).sum(1)
+        ss = (sk * sk).sum(1)
+        yy = (yk * yk).sum(1)
+        delta = torch.where(sy > 0, yy / sy.clamp(min=1e-300), torch.ones_like(sy))
+        # Powell damping: y <- theta y + (1 - theta) delta s when s'y < 0.2 delta s's
+        th = torch.where(sy < 0.2 * delta * ss, 0.8 * delta * ss / (delta * ss - sy).clamp(min=1e-300), torch.ones_like(sy))
+        yk = th.unsqueeze(1) * yk + (1 - th).unsqueeze(1) * delta.unsqueeze(1) * sk
+        use = active & (ss > 1e-24) & torch.isfinite(yk).all(1)
+        M = S.shape[1]
+        full = cnt >= M
+        S = torch.where((use & full).view(-1, 1, 1), torch.roll(S, -1, 1), S)
+        Y = torch.where((use & full).view(-1, 1, 1), torch.roll(Y, -1, 1), Y)
+        slot = torch.where(full, torch.full_like(cnt, M - 1), cnt)
+        rows = torch.nonzero(use).squeeze(1)
+        S[rows, slot[rows]] = sk[rows]
+        Y[rows, slot[rows]] = yk[rows]
+        cnt = torch.where(use & ~full, cnt + 1, cnt)
+        return S, Y, cnt
+
+    def _lbfgs_matrix(self, S, Y, cnt):
+        """Dense B = delta I - [delta S' Y'] [[delta S S', L], [L', -D]]^-1 [delta S; Y] per instance (compact L-BFGS,
+        Byrd / Nocedal / Schnabel 1994), unused slots masked out."""
+        B, M, nf = S.shape
+        dev = S.device
+        valid = (torch.arange(M, device=dev).unsqueeze(0) < cnt.unsqueeze(1)).to(S.dtype)  # [B, M]
+        S, Y = S * valid.unsqueeze(2), Y * valid.unsqueeze(2)
+        last = (cnt - 1).clamp(min=0)
+        rows = torch.arange(B, device=dev)
+        sy_last = (S[rows, last] * Y[rows, last]).sum(1)
+        yy_last = (Y[rows, last] * Y[rows, last]).sum(1)
+        delta = torch.where((cnt > 0) & (sy_last > 0), yy_last / sy_last.clamp(min=1e-300), torch.ones_like(sy_last))
+        SY = torch.bmm(S, Y.transpose(1, 2))                      # s_i' y_j
+        L = torch.tril(SY, diagonal=-1)
+        D = torch.diagonal(SY, dim1=1, dim2=2)
+        SS = torch.bmm(S, S.transpose(1, 2)) * delta.view(-1, 1, 1)
+        inval = torch.diag_embed(1.0 - valid)                    # identity on the unused slots keeps the middle matrix regular
+        top = torch.cat([SS + inval, L], dim=2)
+        bot = torch.cat([L.transpose(1, 2), -torch.diag_embed(D) - inval], dim=2)
+        Mid = torch.cat([top, bot], dim=1)                        # [B, 2M, 2M]
+        Wt = torch.cat([S * delta.view(-1, 1, 1), Y], dim=1)      # [B, 2M, nf]
+        core = torch.linalg.solve(Mid, Wt)
+        Bm = -torch.bmm(Wt.transpose(1, 2), core)
+        di = torch.arange(nf, device=dev)
+        Bm[:, di, di] += delta.unsqueeze(1)
+        return Bm
+
     # ---- solve ---------------------------------------------------------------------------------------
     def solve(self, x0, xl=None, xu=None, chunk=1024):
         """x0: [B, n] starting points; xl/xu: per-instance bounds [B, n] (default: the problem's).
@@ -695,8 +759,15 @@ class BatchedIPM:
             nu = torch.full((B,), 1.0, dtype=torch.float64, device=X.device)  # l1 penalty
             dw_last = torch.zeros(B, dtype=torch.float64, device=X.device)
             iters = torch.zeros(B, dtype=torch.int64, device=X.device)
+            # per-instance filter: (theta, phi) pairs a trial point must not be dominated by; slot 0 holds the upper
+            # bound on the constraint violation, set at the first iteration
+            f_th = torch.full((B, self.filter_slots), float("inf"), dtype=torch.float64, device=X.device)
+            f_ph = torch.full((B, self.filter_slots), float("inf"), dtype=torch.float64, device=X.device)
+            f_n = torch.zeros(B, dtype=torch.int64, device=X.device)
+            th_min = torch.full((B,), -1.0, dtype=torch.float64, device=X.device)
         else:
             lam, zL, zU, mu, nu, dw_last, iters = (state[k] for k in ("lam", "zL", "zU", "mu", "nu", "dw_last", "iters"))
+            f_th, f_ph, f_n, th_min = (state[k] for k in ("f_th", "f_ph", "f_n", "th_min"))
         done = torch.zeros(B, dtype=torch.bool, device=X.device)
         failed = torch.zeros(B, dtype=torch.bool, device=X.device)
         sigma1 = torch.ones(B, dtype=torch.float64, device=X.device)
@@ -714,6 +785,18 @@ class BatchedIPM:
             return phi, c.abs().sum(1)
 
         suspended = None
+        lm = self.hessian == "limited-memory"
+        if lm:
+            if not isinstance(self.kkt, DenseKKT) and state is None:
+                self._setup_fixed = None  # rebuild with the dense step
+                vb, self.var_blocks = self.var_blocks, None
+                self._setup(xl, xu, gl, gu)
+                self.var_blocks = vb
+            M = self.lbfgs_memory
+            lb_S = torch.zeros((B, M, nf), dtype=torch.float64, device=X.device)
+            lb_Y = torch.zeros((B, M, nf), dtype=torch.float64, device=X.device)
+            lb_n = torch.zeros(B, dtype=torch.int64, device=X.device)
+            x_prev = glag_prev = None
         for it in range(it0, self.max_iter):
             g, jv = ev.g_jac(X)
             gradf = ev.grad(X)[:, F]
@@ -725,6 +808,15 @@ class BatchedIPM:
             lam_eq = lam[:, self.eq]
             Jtlam = kkt.Jt(lam_eq)
             rd = gradf + Jtlam - zL + zU
+            if lm:
+                # secant pair of the Lagrangian gradient at the CURRENT multipliers (grad L(x_k, lam_k) - grad L(x_{k-1}, lam_k))
+                if x_prev is not None:
+                    sk = xf - x_prev
+                    yk = (gradf + Jtlam) - (gradf_prev + kkt_Jt_prev(lam_eq))
+                    lb_S, lb_Y, lb_n = self._lbfgs_push(lb_S, lb_Y, lb_n, sk, yk, ~done)
+                x_prev, gradf_prev = xf.clone(), gradf.clone()
+                Jprev = kkt.J.clone()
+                kkt_Jt_prev = lambda v, Jp=Jprev: torch.bmm(Jp.transpose(1, 2), v.unsqueeze(2)).squeeze(2)  # noqa: E731
             compL = torch.where(hasL, sL * zL, torch.zeros_like(sL))
             compU = torch.where(hasU, sU * zU, torch.zeros_like(sU))
             # scaled optimality error (IPOPT eq. (5)-(6)), smax = 100
@@ -750,7 +842,7 @@ class BatchedIPM:
             n_act = int((~done).sum())
             if B >= 16 and n_act < self.compact_at * B:  # resume on the unconverged instances only
                 suspended = {"X": X, "lam": lam, "zL": zL, "zU": zU, "mu": mu, "nu": nu, "dw_last": dw_last, "iters": iters,
-                             "active": ~done, "it": it}
+                             "f_th": f_th, "f_ph": f_ph, "f_n": f_n, "th_min": th_min, "active": ~done, "it": it}
                 break
             # barrier update (monotone): while E_mu <= kappa_eps * mu
             for _ in range(1):
@@ -759,9 +851,16 @@ class BatchedIPM:
                 if not bool(upd.any()):
                     break
                 mu = torch.where(upd, torch.clamp(torch.minimum(0.2 * mu, mu ** 1.5), min=self.tol / 10.0), mu)
+                # a new barrier problem: its filter starts empty (the objective phi_mu changed)
+                f_th = torch.where(upd.unsqueeze(1), torch.full_like(f_th, float("inf")), f_th)
+                f_ph = torch.where(upd.unsqueeze(1), torch.full_like(f_ph, float("inf")), f_ph)
+                f_n = torch.where(upd, torch.zeros_like(f_n), f_n)
             mu_c = mu.unsqueeze(1)
             # Hessian of the Lagrangian (exact, finite differences of the reference scheme) + Sigma
-            hv = ev.hess(X, sigma1, lam)
+            if self.hessian == "limited-memory":
+                hv = self._lbfgs_matrix(lb_S, lb_Y, lb_n)
+            else:
+                hv = ev.hess(X, sigma1, lam)
             Sigma = torch.where(hasL, zL / sL, torch.zeros_like(sL)) + torch.where(hasU, zU / sU, torch.zeros_like(sU))
             rhs1 = gradf + Jtlam - torch.where(hasL, mu_c / sL, torch.zeros_like(sL)) + torch.where(hasU, mu_c / sU, torch.zeros_like(sU))
             dx, dlam, dw, kfail = kkt.step(hv, Sigma, rhs1, c, dw_last, done)
@@ -779,28 +878,69 @@ class BatchedIPM:
             rz = torch.where(hasL & (dzL < 0), -tau * zL / dzL, rz)
             rz = torch.minimum(rz, torch.where(hasU & (dzU < 0), -tau * zU / dzU, torch.full_like(dx, inf)))
             a_z = torch.clamp(rz.amin(1), max=1.0)
-            # l1 merit: phi_mu(x) + nu |c|_1, Armijo backtracking
-            lam_new_inf = (lam_eq + dlam).abs().amax(1)
-            nu = torch.where(nu < lam_new_inf + 1.0, lam_new_inf * 1.5 + 1.0, nu)
             gphi = gradf - torch.where(hasL, mu_c / sL, torch.zeros_like(sL)) + torch.where(hasU, mu_c / sU, torch.zeros_like(sU))
             c1 = c.abs().sum(1)
-            dphi = (gphi * dx).sum(1) - nu * c1
+            gd = (gphi * dx).sum(1)
             phi0, _ = barrier_obj(X, mu)
-            merit0 = phi0 + nu * c1
             alpha = a_max.clone()
             accepted = done.clone()
             Xn = X.clone()
-            for _ls in range(25):
-                Xt = X.clone()
-                Xt[:, F] = xf + alpha.unsqueeze(1) * dx
-                phit, ct = barrier_obj(Xt, mu)
-                ok = (phit + nu * ct <= merit0 + 1e-8 * alpha * torch.clamp(dphi, max=0.0) + 1e-12 * merit0.abs()) & torch.isfinite(phit)
-                take = ok & ~accepted
-                Xn[take] = Xt[take]
-                accepted |= take
-                if bool(accepted.all()):
-                    break
-                alpha = torch.where(accepted, alpha, alpha * 0.5)
+            if self.linesearch == "filter":
+                g_th, g_ph, eta, delta, s_th, s_ph = 1e-5, 1e-8, 1e-8, 1.0, 1.1, 2.3
+                first = th_min < 0
+                th_min = torch.where(first, 1e-4 * torch.clamp(c1, min=1.0), th_min)
+                th_max = 1e4 * torch.clamp(c1, min=1.0)
+                init = first | (f_n == 0)  # an empty filter only bounds the constraint violation
+                f_th[:, 0] = torch.where(init, th_max, f_th[:, 0])
+                f_ph[:, 0] = torch.where(init, torch.full_like(phi0, -float("inf")), f_ph[:, 0])
+                f_n = torch.where(init, torch.ones_like(f_n), f_n)
+                ftype = torch.zeros_like(done)
+                a_min_ls = 1e-9
+                for _ls in range(40):
+                    Xt = X.clone()
+                    Xt[:, F] = xf + alpha.unsqueeze(1) * dx
+                    phit, tht = barrier_obj(Xt, mu)
+                    finite = torch.isfinite(phit) & torch.isfinite(tht)
+                    # not dominated by any filter entry
+                    in_filter = ((tht.unsqueeze(1) >= (1 - g_th) * f_th) & (phit.unsqueeze(1) >= f_ph - g_ph * f_th)).any(1)
+                    switching = (gd < 0) & (alpha * (-gd).clamp(min=0) ** s_ph > delta * c1 ** s_th) & (c1 <= th_min)
+                    armijo = phit <= phi0 + eta * alpha * gd + 1e-13 * phi0.abs()
+                    # h-type step: less constraint violation, or a better barrier objective -- the latter only while the
+                    # violation at most doubles (there is no restoration phase to recover from a run-away of theta)
+                    progress = (tht <= (1 - g_th) * c1) | ((phit <= phi0 - g_ph * c1) & (tht <= torch.maximum(2.0 * c1, th_min)))
+                    ok = finite & ~in_filter & torch.where(switching, armijo, progress)
+                    take = ok & ~accepted
+                    Xn[take] = Xt[take]
+                    ftype = torch.where(take, switching & armijo, ftype)
+                    accepted |= take
+                    if bool(accepted.all()) or float(alpha[~accepted].max()) < a_min_ls:
+                        break
+                    alpha = torch.where(accepted, alpha, alpha * 0.5)
+                # accepted h-type steps (and f-type steps that did not satisfy Armijo) augment the filter
+                aug = accepted & ~done & ~ftype
+                if bool(aug.any()):
+                    slot = torch.where(f_n < self.filter_slots, f_n, torch.ones_like(f_n))  # full: overwrite from slot 1 on (slot 0 = bound)
+                    rows = torch.nonzero(aug).squeeze(1)
+                    f_th[rows, slot[rows]] = ((1 - g_th) * c1)[rows]
+                    f_ph[rows, slot[rows]] = (phi0 - g_ph * c1)[rows]
+                    f_n = torch.where(aug, torch.where(f_n < self.filter_slots, f_n + 1, torch.full_like(f_n, 2)), f_n)
+            else:
+                # l1 merit: phi_mu(x) + nu |c|_1, Armijo backtracking
+                lam_new_inf = (lam_eq + dlam).abs().amax(1)
+                nu = torch.where(nu < lam_new_inf + 1.0, lam_new_inf * 1.5 + 1.0, nu)
+                dphi = gd - nu * c1
+                merit0 = phi0 + nu * c1
+                for _ls in range(25):
+                    Xt = X.clone()
+                    Xt[:, F] = xf + alpha.unsqueeze(1) * dx
+                    phit, ct = barrier_obj(Xt, mu)
+                    ok = (phit + nu * ct <= merit0 + 1e-8 * alpha * torch.clamp(dphi, max=0.0) + 1e-12 * merit0.abs()) & torch.isfinite(phit)
+                    take = ok & ~accepted
+                    Xn[take] = Xt[take]
+                    accepted |= take
+                    if bool(accepted.all()):
+                        break
+                    alpha = torch.where(accepted, alpha, alpha * 0.5)
             # instances whose line search failed: take the tiny step anyway and raise dw next time
             stuck = ~accepted
             if bool(stuck.any()):
@@ -808,6 +948,10 @@ class BatchedIPM:
                 Xt[:, F] = xf + alpha.unsqueeze(1) * dx
                 Xn[stuck] = Xt[stuck]
                 dw_last = torch.where(stuck, torch.clamp(dw_last * 100.0, min=1e-2), dw_last)
+                if self.linesearch == "filter":  # restart the filter of a stuck instance
+                    f_th = torch.where(stuck.unsqueeze(1), torch.full_like(f_th, float("inf")), f_th)
+                    f_ph = torch.where(stuck.unsqueeze(1), torch.full_like(f_ph, float("inf")), f_ph)
+                    f_n = torch.where(stuck, torch.zeros_like(f_n), f_n)
             self._last_alpha = alpha
             act = (~done).unsqueeze(1)
             a_col = alpha.unsqueeze(1)

@@ -55,3 +55,34 @@ def test_adaptive_loop_brachistochrone_with_host_outer_solver_on_gpu():
     assert hist[-1]["n"] > hist[0]["n"] and x.size == hist[-1]["n"]
     # the refined mesh reproduces the fine fixed-mesh optimum of the same functor (tests/test_host_outer_loop.py)
     assert abs(hist[-1]["objective"] - 0.824338669) <= 1e-8
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("method", ["ph", "hp-Liu"])
+def test_adaptive_loop_reference_hypersensitive_horizon_gpu_resident(method):
+    """The reference's hypersensitive example as shipped (t_f = 5000, HyperSensitive.cpp:17; the example itself selects
+    hp-Liu, :56) through the whole mesh loop with the GPU-resident outer solver, by both refinement methods: the
+    boundary layers are found, the objective settles at the value the refined meshes agree on."""
+    from lpopc_b200 import nlp, solver
+    op = examples.hypersensitive(intervals=20, nodes=6)
+    x, hist = adaptive.solve_adaptive(op, nlp.TranscribedNLP, solver.CudaEvaluator, solver.BatchedIPM, mesh_tol=1e-6, max_grids=10,
+                                      method=method, max_iter=300)
+    assert all(h["status"] == 0 for h in hist) and len(hist) >= 5
+    # hp-Liu resolves the layers with ~100 nodes by grid 7 (error estimate at the tolerance); ph adds nodes more slowly
+    assert min(abs(h["objective"] - 1.3308068) for h in hist[3:]) <= (2e-6 if method == "hp-Liu" else 5e-4)
+    assert min(h["max_rel_error"] for h in hist) <= 1e-4 * hist[0]["max_rel_error"]
+    assert len({tuple(h["nodes"]) for h in hist}) >= 4  # the mesh really changed from grid to grid
+    if method == "hp-Liu":
+        assert min(h["nodes"][0] for h in hist[5:]) < hist[0]["nodes"][0]  # it also removes nodes where they are not needed
+
+
+@pytest.mark.gpu
+def test_adaptive_loop_brachistochrone_gpu_resident_solver():
+    """Free final time with the GPU-RESIDENT outer solver (filter line search): no host solver in the loop."""
+    from lpopc_b200 import nlp, solver
+    op = examples.brachistochrone(intervals=2, nodes=4)
+    # mesh tolerance above the solver's KKT tolerance (1e-6): the error estimate cannot fall below the solve's own accuracy
+    x, hist = adaptive.solve_adaptive(op, nlp.TranscribedNLP, solver.CudaEvaluator, solver.BatchedIPM, mesh_tol=1e-5, max_grids=8, max_iter=200)
+    assert all(h["status"] == 0 for h in hist) and len(hist) >= 2
+    assert hist[-1]["mesh_satisfied"] and hist[-1]["max_rel_error"] <= 1e-5 < hist[0]["max_rel_error"]
+    assert abs(hist[-1]["objective"] - 0.824338669) <= 1e-7

@@ -7,6 +7,8 @@ oracle/_ref/liblpopc_ref.so (oracle/ref_build.mk).  Integers must be equal; valu
 relative (Armadillo's dense-product summation order is the one thing the stand-in cannot pin).
 Skipped when neither /root/reference nor a prebuilt oracle/_ref exists.
 """
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -63,3 +65,32 @@ def test_dependency_probe_equals_reference():
     for a, b in zip(o.h_structure(), r.h_structure()):
         assert np.array_equal(a, b)
     assert rel(o.eval_h(x, sigma, lam), r.eval_h(x, sigma, lam)) <= 1e-9
+
+
+@pytest.mark.parametrize("name,new", [("hypersensitive/u8x4", "hypersensitive/ragged"), ("bryson_denham/u7x6", "bryson_denham/ragged"),
+                                      ("launch/u5x4", "launch/ragged")])
+def test_guess_transfer_between_grids_matches_the_reference(name, new):
+    """Warm start of the mesh loop: the solution on one grid becomes the user guess (time, states, controls with the
+    spline end row; Nlp2OPConverter.cpp:160-193) and the reference's GetGuess interpolates it onto the next grid with its
+    natural cubic spline (LpGuessChecker.cpp:130-190, 208-294).  lpopc_b200.adaptive.transfer_guess must land on the
+    same starting point."""
+    from lpopc_b200 import adaptive
+    op = cases.build(name)
+    r = RefOracle(op)
+    _, x, _, lam = cases.inputs(op, r, 13)
+    res, _ = r.nlp2op(x, lam)  # the reference's own converted solution: time grid, states, controls incl. the end row
+    old_pts = [r.tables(ip)["points"] for ip in range(len(op.phases))]
+    op_new = cases.build(new)
+    r_new = RefOracle(op_new)
+    for ip, q in enumerate(res):
+        t = np.ascontiguousarray(q["time"])
+        xs = np.ascontiguousarray(q["state"].T).reshape(-1)
+        us = np.ascontiguousarray(q["control"].T).reshape(-1) if q["control"].size else np.zeros(1)
+        r_new._check(r_new.L.lpo_set_guess(r_new.h, C.c_int(ip), C.c_int(t.size), t.ctypes.data_as(C.POINTER(C.c_double)),
+                                           xs.ctypes.data_as(C.POINTER(C.c_double)), us.ctypes.data_as(C.POINTER(C.c_double))))
+    r_new.refresh()
+    ref_start = r_new.guess()
+    new_pts = [r_new.tables(ip)["points"] for ip in range(len(op.phases))]
+    mine = adaptive.transfer_guess(op, x, old_pts, new_pts, [q["control"][-1] if q["control"].size else np.zeros(0) for q in res])
+    assert mine.shape == ref_start.shape
+    assert np.max(np.abs(mine - ref_start) / np.maximum(1.0, np.abs(ref_start))) <= 1e-13

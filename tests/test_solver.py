@@ -180,3 +180,40 @@ def test_fused_block_tridiagonal_solve_matches_library(B, K, nb, nbd):
         torch.cuda.synchronize()
         inf = info.cpu()
         assert rc == 0 and int(inf[1]) > (K - 1) * nb and int(inf[0]) == 0 and bool(torch.isfinite(torch.tril(Lall[1])).all())
+
+
+@pytest.mark.parametrize("problem,optimum,rtol", [("bryson_denham", 4.0, 1e-6), ("brachistochrone", 0.824338669, 1e-8)])
+def test_ipm_filter_line_search_solves_free_final_time_problems_cpu(problem, optimum, rtol):
+    """The reference solves its free-final-time examples with IPOPT's filter line search (LpNLPSolver.cpp:27-33 leaves the
+    default; Lpopc/example/bryson-denham/BrysonDenham.cpp:77-78).  With the l1 merit function the iteration stalls on
+    them (steps of 2^-10); the filter line search converges -- to the literature optimum 4 / (9 l), l = 1/9, of
+    Bryson-Denham and to the fine-mesh brachistochrone value -- alone and in a batch, from perturbed starts too."""
+    op = getattr(examples, problem)(intervals=2, nodes=6)
+    ev = OracleEvaluator(op)
+    x0 = op.guess([ev.o.tables(0)["points"]])
+    X0 = np.stack([x0, x0, x0 * 1.01])
+    r = solver.BatchedIPM(ev, tol=1e-6, max_iter=150).solve(X0)
+    assert r["status"].tolist() == [0, 0, 0] and float(r["kkt_error"].max()) <= 1e-6
+    assert np.allclose(r["obj"].numpy(), optimum, rtol=rtol, atol=0)
+    assert int(r["iters"].max()) <= 60
+    stalled = solver.BatchedIPM(ev, tol=1e-6, max_iter=60, linesearch="merit").solve(x0[None, :])
+    assert problem != "brachistochrone" or int(stalled["status"][0]) == 1  # what the filter is there for
+
+
+@pytest.mark.parametrize("problem,kw", [("hypersensitive", dict(intervals=4, nodes=6)), ("brachistochrone", dict(intervals=2, nodes=6)),
+                                        ("cartpole", dict(intervals=3, nodes=5))])
+def test_ipm_limited_memory_hessian_mode_cpu(problem, kw):
+    """hessian = "limited-memory" (the reference's default "hessian-approximation", LpNLPSolver.cpp:30-33): damped L-BFGS
+    on the Lagrangian gradient, no eval_h call, same converged objective as the exact-Hessian mode."""
+    op = getattr(examples, problem)(**kw)
+    ev = OracleEvaluator(op)
+    calls = {"h": 0}
+    hess = ev.hess
+    ev.hess = lambda *a: (calls.__setitem__("h", calls["h"] + 1), hess(*a))[1]
+    x0 = op.guess([ev.o.tables(0)["points"]])
+    X0 = np.stack([x0, x0 * 1.01])
+    lm = solver.BatchedIPM(ev, tol=1e-6, max_iter=300, hessian="limited-memory").solve(X0)
+    assert calls["h"] == 0 and lm["status"].tolist() == [0, 0]
+    ex = solver.BatchedIPM(ev, tol=1e-6, max_iter=150).solve(X0)
+    assert calls["h"] > 0 and ex["status"].tolist() == [0, 0]
+    assert np.allclose(lm["obj"].numpy(), ex["obj"].numpy(), rtol=1e-6)
