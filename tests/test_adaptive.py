@@ -16,7 +16,7 @@ def test_transfer_guess_reproduces_smooth_profiles():
     f = [lambda t: 1 + 0.5 * t, lambda t: np.sin(t), lambda t: t ** 2, lambda t: np.cos(2 * t)]
     tau_o, tau_n = np.concatenate([old[0], [1.0]]), np.concatenate([new[0], [1.0]])
     x = np.concatenate([f[0](tau_o), f[1](tau_o), f[2](tau_o), f[3](tau_o[:-1]), [0.0, 7.5]])
-    y = adaptive.transfer_guess(op, x, old, new)
+    y = adaptive.transfer_guess(op, x, old, new, control_end=[[f[3](1.0)]])  # the control's end row comes from lpb_nlp2op in the loop
     assert y.size == 3 * 23 + 22 + 2 and np.array_equal(y[-2:], [0.0, 7.5])
     assert np.allclose(y[:23], f[0](tau_n), atol=1e-12)          # linear profiles are reproduced exactly
     assert np.allclose(y[23:46], f[1](tau_n), atol=2e-2)
