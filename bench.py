@@ -42,11 +42,11 @@ SOLVE_INSTANCES = 4096  # per GPU, for the solves/s side measurement
 MESH_INTERVALS, MESH_NODES = 8, 8
 NBUF = 4  # rotating input sets so that x is not served from L2 between steps
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_cons_jac launch of this workload (4096 instances)
-# from the committed `ncu --set full` capture (35.76 MB read + 622.69 MB written; below the 713 MB algorithmic figure
+# from the committed `ncu --set full` capture (35.23 MB read + 621.77 MB written; below the 713 MB algorithmic figure
 # because part of the last stores is still in L2 at kernel end).  DRAM counters cannot be read outside a profiler, so
 # this is NOT measured in the bench run; the line says where it comes from.
-NCU_TRAFFIC_BYTES = 658450944
-NCU_TRAFFIC_SOURCE = "profiles/r01_cons_jac_full.txt (ncu --set full of this kernel on this workload; not measured in this run)"
+NCU_TRAFFIC_BYTES = 657005824
+NCU_TRAFFIC_SOURCE = "profiles/r02_cons_jac_full.txt (ncu --set full of this kernel on this workload; not measured in this run)"
 STRONG_TOTAL = 4096  # BASELINE config 4 as written: 4096 instances in total, sharded over the ranks
 C5_INTERVALS, C5_NODES = 10000, 10  # BASELINE config 5: synthetic ns=20 / nc=6 dynamics on 100k LGR nodes
 
