@@ -83,8 +83,10 @@ class ClockSampler:
     (same counters as the nvidia-smi clocks line of B200_PROFILING.md; nvidia-smi's own 100 ms
     period is longer than a short timed region)."""
 
-    def __init__(self, index):
+    def __init__(self, index, period_s=0.0):
         self.index = index
+        self.period_s = period_s  # 0: poll back to back (millisecond-long timed regions); the polling thread holds the GIL
+                                  # while it runs, so regions that execute Python for seconds use a few milliseconds
         self.samples = []
         self.stop_flag = threading.Event()
         self.thread = None
@@ -112,7 +114,7 @@ class ClockSampler:
             except Exception as e:
                 self.err = repr(e)
                 return
-            time.sleep(0)  # yield; NVML itself takes a few tens of microseconds per query
+            time.sleep(self.period_s)  # 0 = yield only; NVML itself takes a few tens of microseconds per query
 
     def stop(self):
         if self.thread is None:
@@ -130,7 +132,7 @@ class ClockSampler:
                     reasons.add(nm)
         sm = [x for x, _ in self.samples]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(smax), "reasons": sorted(reasons),
-                "samples": len(sm), "source": "NVML polled back to back inside the timed region"}
+                "samples": len(sm), "source": "NVML polled %s inside the timed region" % ("back to back" if self.period_s == 0 else "every %g ms" % (1e3 * self.period_s))}
 
 
 REF_LIB = os.path.join(ROOT, "oracle", "_ref", "liblpopc_ref.so")
@@ -581,11 +583,20 @@ def main():
         ipm = solver.BatchedIPM(ev, tol=1e-6, max_iter=150, var_blocks=solver.interval_blocks(op, ev.n))
         ipm.solve(X0[:8], XL[:8], XU[:8])  # warm-up
         barrier()
-        solve_sampler = ClockSampler(local_rank)
+        solve_sampler = ClockSampler(local_rank, period_s=0.005)  # back-to-back polling would steal the GIL from the solver's Python loop
         solve_sampler.start()
         ts = time.perf_counter()
+        _prof = None
+        if os.environ.get("LPB_BENCH_PROFILE_SOLVE"):  # development: where does the solve spend its host time?
+            import cProfile
+            _prof = cProfile.Profile()
+            _prof.enable()
         res = ipm.solve(X0, XL, XU, chunk=SOLVE_INSTANCES)
         torch.cuda.synchronize()
+        if _prof is not None:
+            import pstats
+            _prof.disable()
+            pstats.Stats(_prof, stream=sys.stderr).sort_stats("tottime").print_stats(16)
         t_own = time.perf_counter() - ts  # this rank's own solve time (the barrier below waits for the slowest rank)
         barrier()
         t_solve = torch.tensor([time.perf_counter() - ts], dtype=torch.float64, device=dev)
@@ -602,7 +613,7 @@ def main():
         solves = {"metric": "batched OCP solves/s", "value": float(n_ok.item()) / float(t_solve.item()), "unit": "solves/s",
                   "instances": ns_ * world, "converged": int(n_ok.item()), "seconds": float(t_solve.item()),
                   "iters_mean": float(it_sum.item()) / (ns_ * world), "tol": 1e-6, "nnz_h_probed": ev.nnz_h,
-                  "clocks_rank0": {k: solve_clocks.get(k) for k in ("sm_mhz", "sm_max_mhz", "reasons")},
+                  "clocks_rank0": {k: solve_clocks.get(k) for k in ("sm_mhz", "sm_max_mhz", "reasons", "samples")},
                   "seconds_per_rank": [round(v, 3) for v in per_rank[:, 0].tolist()], "iters_max_per_rank": [int(v) for v in per_rank[:, 1].tolist()],
                   "solver": "lockstep primal-dual interior point, exact FD Hessian, KKT step: %s; block solves = lpb_blocktri_solve "
                             "(one launch per solve), factorisation = %s; NLP callbacks = device-resident transcription kernels"

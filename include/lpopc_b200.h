@@ -209,8 +209,22 @@ int lpb_structure_dev(lpb_handle* h, const int** d_jac_iRow, const int** d_jac_j
  * supported (caller falls back to library routines), or a CUDA error code - 1000. */
 int lpb_blocktri_factor(int B, int K, int nb, int nbd, const double* Dp, const double* Ep, const int* bnd, double* L, double* C,
                         int* info, void* cuda_stream);
+/* Assembly + factorisation of the block-tridiagonal KKT matrix of the batched interior-point step in one launch
+ * (k_kkt_factor, lpb_blocktri.cu): A_i = D_i + diag(diag_i + dw) + gamma Jb_i^T Jb_i with the boundary coupling of the
+ * neighbouring intervals, L_i L_i^T = A_i, C_i = E_i' L_i^-T, and the inertia-correction retry (larger dw until every
+ * pivot is positive) per instance.  Device pointers; D [B][K][nb][nb], E [B][max(K-1,1)][nbd][nb], Jb [B][K][mr][nb+nbd],
+ * diag [B][K][nb], active [B] bytes (0: converged instance, identity factors are written and its info is 0), dw [B]
+ * in/out, L / C like D / E, info [B].  Returns 0, -1 (shape not supported) or a negative cudaError_t - 1000.
+ * No counterpart in the reference (IPOPT + MUMPS do this on the host). */
+int lpb_kkt_factor(int B, int K, int nb, int nbd, int mr, double gamma, const double* D, const double* E, const double* Jb, const double* diag,
+                   const int* bnd, const unsigned char* active, double* dw, double* L, double* C, int* info, void* stream);
 int lpb_blocktri_solve(int B, int K, int nb, int nbd, const double* const* L, const double* const* C, long long strideL,
                        long long strideC, const int* bnd, const double* rhs, double* out, void* cuda_stream);
+/* lpb_blocktri_solve with a per-instance mask: active [B] bytes on the device (or null); instances with 0 are skipped
+ * and get a zero solution. */
+int lpb_blocktri_solve_masked(int B, int K, int nb, int nbd, const double* const* L, const double* const* C, long long strideL,
+                              long long strideC, const int* bnd, const unsigned char* active, const double* rhs, double* out,
+                              void* cuda_stream);
 
 /* Tuning / introspection (not part of the reference boundary). */
 int lpb_set_option_int(lpb_handle* h, const char* name, int value);

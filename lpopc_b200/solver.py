@@ -354,6 +354,13 @@ class BlockTridiagKKT:
             out[:, 1:, self.bnd] += y[:, :-1, self.nb:]
         return out
 
+    def _Jtmul2(self, va, vb):  # J^T va and J^T vb in one sweep over the Jacobian blocks
+        y = torch.einsum("bkmn,bkmr->bknr", self.Jb, torch.stack([va, vb], 3))
+        out = y[:, :, :self.nb].clone()
+        if self.K > 1:
+            out[:, 1:, self.bnd] += y[:, :-1, self.nb:]
+        return out[..., 0], out[..., 1]
+
     def Jt(self, v):
         return self.from_blocks(self._Jtmul(self.dual_to_blocks(v)))
 
@@ -418,7 +425,7 @@ class BlockTridiagKKT:
             prev = L
         return Ls, Cs, info
 
-    def _solve_fused(self, Ls, Cs, rb):
+    def _solve_fused(self, Ls, Cs, rb, active=None):
         """The whole forward/backward block substitution in ONE launch (lpb_blocktri_solve, csrc/lpb_blocktri.cu)
         instead of 2K library triangular solves.  None if the extension or the shape is not available."""
         if not rb.is_cuda or self.fused_solve is False:
@@ -443,8 +450,9 @@ class BlockTridiagKKT:
         if any(L.stride(0) != sL or L.stride(1) != nb or L.stride(2) != 1 for L in Ls) or \
                 any(c.stride(0) != sC or c.stride(1) != nb or c.stride(2) != 1 for c in Cs):
             return None
-        rc = self._lib.lpb_blocktri_solve(B, K, nb, self.nbd, Lp, Cp, sL, sC, C.c_void_p(self._bnd32.data_ptr()), C.c_void_p(rb.data_ptr()),
-                                          C.c_void_p(out.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        rc = self._lib.lpb_blocktri_solve_masked(B, K, nb, self.nbd, Lp, Cp, sL, sC, C.c_void_p(self._bnd32.data_ptr()),
+                                                 C.c_void_p(active.data_ptr() if active is not None else None), C.c_void_p(rb.data_ptr()),
+                                                 C.c_void_p(out.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream))
         if rc == -1:
             self.fused_solve = False  # shape not supported: library solves from now on
             return None
@@ -452,9 +460,10 @@ class BlockTridiagKKT:
             raise RuntimeError("lpb_blocktri_solve failed: %d" % rc)
         return out
 
-    def _solve(self, Ls, Cs, rb):
+    def _solve(self, Ls, Cs, rb, active=None):
+        """active: optional uint8 [B] on the device; the fused kernel skips instances with 0 (their solution is zero)."""
         self.n_solve += 1
-        fused = self._solve_fused(Ls, Cs, rb)
+        fused = self._solve_fused(Ls, Cs, rb, active)
         if fused is not None:
             return fused
         bi = self.bnd
@@ -473,6 +482,67 @@ class BlockTridiagKKT:
             xs[i] = torch.linalg.solve_triangular(Ls[i].transpose(1, 2), t.unsqueeze(2), upper=True).squeeze(2)
         return torch.stack(xs, 1)
 
+    def _assemble_and_factor(self, D, E, base, dw, done):
+        """Library path of the assembly + factorisation (einsum, elementwise assembly, batched Cholesky, one more round
+        per inertia-correction retry): the reference of lpb_kkt_factor and the fallback where it does not apply."""
+        B, K, nb, nbd, g = D.shape[0], self.K, self.nb, self.nbd, self.gamma
+        bi = self.bnd
+        di = torch.arange(nb, device=D.device)
+        G = torch.einsum("bkmi,bkmj->bkij", self.Jb, self.Jb)  # J_i^T J_i over [own block | boundary of block i+1]
+        Dp = D + g * G[:, :, :nb, :nb]
+        if K > 1 and nbd > 0:
+            Dp[:, 1:, bi.unsqueeze(1), bi.unsqueeze(0)] += g * G[:, :-1, nb:, nb:]
+            Ep = E + g * G[:, :-1, nb:, :nb]
+        else:
+            Ep = E
+        Gd = torch.diagonal(G, dim1=2, dim2=3)  # [B, K, nb + nbd]
+        gdiag = g * Gd[:, :, :nb].clone()
+        if K > 1 and nbd > 0:
+            gdiag[:, 1:, bi] += g * Gd[:, :-1, nb:]
+        for _try in range(40):
+            Dp[:, :, di, di] = base + gdiag + dw.view(-1, 1, 1)
+            Ls, Cs, info = self._factor(Dp, Ep)
+            bad = (info != 0) & (~done)
+            if not bool(bad.any()):
+                break
+            dw = torch.where(bad, torch.where(dw == 0, torch.full_like(dw, 1e-4), dw * (100.0 if _try < 2 else 8.0)), dw)
+        return Ls, Cs, info, dw
+
+    def _kkt_factor_fused(self, D, E, diag_add, dw0, done):
+        """lpb_kkt_factor: assembly (gamma J^T J, boundary coupling), block Cholesky and the inertia-correction retry in
+        ONE launch.  None where it does not apply (CPU tensors, unsupported shape)."""
+        if not D.is_cuda or self.fused_solve is False:
+            return None
+        import ctypes as C
+        if self.fused_solve is None:
+            try:
+                from . import nlp
+                self._lib = nlp.load_library()
+                self._bnd32 = self.bnd.to(torch.int32).contiguous()
+                self.fused_solve = True
+            except Exception:
+                self.fused_solve = False
+                return None
+        if getattr(self, "_kkt_fused_off", False):
+            return None
+        B, K, nb, nbd = D.shape[0], self.K, self.nb, self.nbd
+        D, E, Jb, dg = D.contiguous(), E.contiguous(), self.Jb.contiguous(), diag_add.contiguous()
+        Lall = torch.empty_like(D)
+        Call = torch.empty_like(E)
+        info = torch.empty(B, dtype=torch.int32, device=D.device)
+        active = (~done).to(torch.uint8).contiguous()
+        dw = dw0.clone().contiguous()
+        rc = self._lib.lpb_kkt_factor(B, K, nb, nbd, self.mr, C.c_double(self.gamma), C.c_void_p(D.data_ptr()), C.c_void_p(E.data_ptr()),
+                                      C.c_void_p(Jb.data_ptr()), C.c_void_p(dg.data_ptr()), C.c_void_p(self._bnd32.data_ptr()),
+                                      C.c_void_p(active.data_ptr()), C.c_void_p(dw.data_ptr()), C.c_void_p(Lall.data_ptr()),
+                                      C.c_void_p(Call.data_ptr()), C.c_void_p(info.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        if rc == -1:
+            self._kkt_fused_off = True
+            return None
+        if rc != 0:
+            raise RuntimeError("lpb_kkt_factor failed: %d" % rc)
+        return [Lall[:, i] for i in range(K)], [Call[:, i] for i in range(K - 1)], info, dw
+
     def step(self, hv, Sigma, rhs1, c, dw_last, done):
         B, K, nb, nbd, g = hv.shape[0], self.K, self.nb, self.nbd, self.gamma
         dev = hv.device
@@ -486,37 +556,36 @@ class BlockTridiagKKT:
         E = E.view(B, max(K - 1, 1), nbd, nb)
         di = torch.arange(nb, device=dev)
         base = D[:, :, di, di] + self.to_blocks(Sigma) + self.pad_diag
-        G = torch.einsum("bkmi,bkmj->bkij", self.Jb, self.Jb)  # J_i^T J_i over [own block | boundary of block i+1]
-        Dp = D + g * G[:, :, :nb, :nb]
-        if K > 1 and nbd > 0:
-            Dp[:, 1:, bi.unsqueeze(1), bi.unsqueeze(0)] += g * G[:, :-1, nb:, nb:]
-            Ep = E + g * G[:, :-1, nb:, :nb]
-        else:
-            Ep = E
         dw = torch.where(dw_last > 0, dw_last / 3.0, torch.zeros_like(dw_last))
         dw = torch.where(dw < 1e-9, torch.zeros_like(dw), dw)
-        Gd = torch.diagonal(G, dim1=2, dim2=3)  # [B, K, nb + nbd]
-        gdiag = g * Gd[:, :, :nb].clone()
-        if K > 1 and nbd > 0:
-            gdiag[:, 1:, bi] += g * Gd[:, :-1, nb:]
-        for _try in range(40):
-            Dp[:, :, di, di] = base + gdiag + dw.view(-1, 1, 1)
-            Ls, Cs, info = self._factor(Dp, Ep)
-            bad = (info != 0) & (~done)
-            if not bool(bad.any()):
-                break
-            dw = torch.where(bad, torch.where(dw == 0, torch.full_like(dw, 1e-4), dw * (100.0 if _try < 2 else 8.0)), dw)
+        fused = self._kkt_factor_fused(D, E, base - D[:, :, di, di], dw, done) if self.fused_factor else None
+        if fused is not None:
+            Ls, Cs, info, dw = fused
+        else:
+            Ls, Cs, info, dw = self._assemble_and_factor(D, E, base, dw, done)
         D[:, :, di, di] = base + dw.view(-1, 1, 1)  # H = W + Sigma + dw I (exact system of the refinement)
         r1b, cb = self.to_blocks(rhs1), self.dual_to_blocks(c)
-        dxb = torch.zeros_like(r1b)
-        dlb = torch.zeros_like(cb)
-        for _ in range(1 + self.refine):
-            res1 = -r1b - (self._Hmul(D, E, dxb) + self._Jtmul(dlb))
-            res2 = -cb - self._Jmul(dxb)
-            ddx = self._solve(Ls, Cs, res1 + g * self._Jtmul(res2))
-            ddl = g * (self._Jmul(ddx) - res2)
+        active = (~done).to(torch.uint8).contiguous()
+        # iterative refinement on  [H J^T; J 0] [dx; dl] = -[r1; c].  H dx, J dx and J^T dl are carried along as running
+        # sums of the products with the corrections (linear in them), so a pass costs one H product and two sweeps over
+        # the dense Jacobian blocks (J ddx, and J^T [ddl, res2] in one) instead of one H product and four sweeps
+        dxb, dlb = torch.zeros_like(r1b), torch.zeros_like(cb)
+        Hdx, Jdx, Jtdl = torch.zeros_like(r1b), torch.zeros_like(cb), torch.zeros_like(r1b)
+        res2 = -cb
+        Jt_res2 = self._Jtmul(res2)
+        for it in range(1 + self.refine):
+            res1 = -r1b - (Hdx + Jtdl)
+            ddx = self._solve(Ls, Cs, res1 + g * Jt_res2, active)
+            Jddx = self._Jmul(ddx)
+            ddl = g * (Jddx - res2)
             dxb = dxb + ddx
             dlb = dlb + ddl
+            if it < self.refine:
+                Hdx = Hdx + self._Hmul(D, E, ddx)
+                Jdx = Jdx + Jddx
+                res2 = -cb - Jdx
+                Jt_ddl, Jt_res2 = self._Jtmul2(ddl, res2)
+                Jtdl = Jtdl + Jt_ddl
         failed = (info != 0) & (~done)  # still indefinite after the last regularisation try: status 2, not a silent step
         return self.from_blocks(dxb), self.dual_from_blocks(dlb), dw, failed
 

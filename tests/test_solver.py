@@ -217,3 +217,51 @@ def test_ipm_limited_memory_hessian_mode_cpu(problem, kw):
     ex = solver.BatchedIPM(ev, tol=1e-6, max_iter=150).solve(X0)
     assert calls["h"] > 0 and ex["status"].tolist() == [0, 0]
     assert np.allclose(lm["obj"].numpy(), ex["obj"].numpy(), rtol=1e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,K,nb,nbd,mr", [(5, 4, 44, 8, 30), (3, 8, 140, 22, 96), (4, 1, 17, 3, 9), (6, 3, 36, 6, 40), (3, 2, 170, 10, 40)])
+def test_kkt_factor_kernel_matches_library_assembly(B, K, nb, nbd, mr):
+    """lpb_kkt_factor (gamma J^T J + boundary coupling + block Cholesky + inertia-correction retry in one launch, one
+    8 x 8 tile of the augmented matrix per thread; 6 x 6 for the last shape, whose 8 x 8 tiling needs more than 8 warps) against the library path it replaces (einsum, elementwise assembly,
+    batched Cholesky, Python retry loop): same factors, same couplings, same regularisation per instance -- on systems
+    that are positive definite as they come, on one that needs the retry, and on a converged (inactive) instance."""
+    from lpopc_b200 import nlp
+    nlp.load_library()
+    dev = torch.device("cuda")
+    gen = torch.Generator(device="cpu").manual_seed(B * 977 + nb)
+    kkt = object.__new__(solver.BlockTridiagKKT)
+    kkt.K, kkt.nb, kkt.nbd, kkt.mr, kkt.gamma = K, nb, nbd, mr, 1e3
+    kkt.bnd = torch.randperm(nb, generator=gen)[:nbd].sort().values.to(dev)
+    kkt.fused_factor, kkt.fused_solve, kkt.n_factor = False, None, 0
+    A = torch.randn(B, K, nb, nb, generator=gen, dtype=torch.float64)
+    D = (A @ A.transpose(2, 3) * 0.05 + 0.5 * torch.eye(nb, dtype=torch.float64)).to(dev)
+    D[1] = D[1] - 50.0 * torch.eye(nb, dtype=torch.float64, device=dev)  # indefinite without regularisation: the retry must find dw
+    E = (0.1 * torch.randn(B, max(K - 1, 1), nbd, nb, generator=gen, dtype=torch.float64)).to(dev)
+    Jb = torch.randn(B, K, mr, nb + nbd, generator=gen, dtype=torch.float64)
+    Jb[:, -1, :, nb:] = 0.0  # the last interval has no next boundary
+    Jb = (Jb * (torch.rand(B, K, mr, nb + nbd, generator=gen) < 0.2)).to(dev)  # sparse like a collocation Jacobian
+    kkt.Jb = Jb
+    sigma = torch.rand(B, K, nb, generator=gen, dtype=torch.float64).to(dev)
+    di = torch.arange(nb, device=dev)
+    base = D[:, :, di, di] + sigma
+    dw0 = torch.zeros(B, dtype=torch.float64, device=dev)
+    dw0[2] = 3e-3
+    done = torch.zeros(B, dtype=torch.bool, device=dev)
+    done[0] = True
+    Lr, Cr, info_r, dw_r = kkt._assemble_and_factor(D.clone(), E.clone(), base, dw0.clone(), done)
+    fused = kkt._kkt_factor_fused(D.clone(), E.clone(), sigma, dw0.clone(), done)
+    assert fused is not None
+    Lf, Cf, info_f, dw_f = fused
+    torch.cuda.synchronize()
+    assert info_f.tolist() == [0] * B and info_r.tolist() == [0] * B
+    assert torch.equal(dw_f, dw_r) and float(dw_f[1]) > 0 and float(dw_f[2]) == 3e-3
+    live = ~done
+    eye = torch.eye(nb, dtype=torch.float64, device=dev)
+    for i in range(K):
+        lr, lf = torch.tril(Lr[i]), torch.tril(Lf[i])
+        assert float((lf[live] - lr[live]).abs().max() / lr[live].abs().max()) <= 1e-10, i
+        assert torch.equal(lf[0], eye)  # the converged instance is not factorised: identity, its step is discarded
+    for i in range(K - 1):
+        assert float((Cf[i][live] - Cr[i][live]).abs().max() / Cr[i][live].abs().max().clamp(min=1e-300)) <= 1e-9, i
+        assert float(Cf[i][0].abs().max()) == 0.0
