@@ -382,8 +382,9 @@ struct lpb_handle {
     // rows and the Doffdiag entries), cached on the host at refresh
     bool err_fresh = false; // mesh-error tables match the current mesh
     MeshErrDev med;
-    DevBuf<double> d_tem, d_abserr, d_conv;
+    DevBuf<double> d_tem, d_abserr, d_conv, d_colmax, d_rel, d_imax;
     std::vector<double> h_ctail;
+    bool ctail_fresh = false;
     int host_fill_const = 1; // option "host_fill_const"
     int host_threads = 0;    // option "host_threads": threads of the constant-tail fill (0 = min(hardware threads / 2, 16))
     // sparse return of the head [NL] (k_return_head): segment table of one instance's head, the segments
@@ -439,11 +440,14 @@ struct lpb_handle {
     int filled_nbatch = 0;
     long long filled_plan = -1, plan_version = 0;
     long long persistent_hits = 0;
+    long long structure_ns = 0; // device time of the two index-map kernels of the last refresh
+    cudaEvent_t ev_struct[2] = {nullptr, nullptr};
     lpb_handle() { std::memset(&pd, 0, sizeof pd); std::memset(&lay, 0, sizeof lay); std::memset(&ltab, 0, sizeof ltab); std::memset(&opts, 0, sizeof opts); }
     ~lpb_handle()
     {
         for (auto* v : {&timed_cons, &timed_hess})
             for (auto& pr : *v) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+        for (cudaEvent_t e : ev_struct) if (e) cudaEventDestroy(e);
         if (own_stream && stream) cudaStreamDestroy(stream);
         if (fp.g_fgj) cudaGraphExecDestroy(fp.g_fgj);
         if (fp.g_h) cudaGraphExecDestroy(fp.g_h);
@@ -596,21 +600,19 @@ static void refresh(lpb_handle* h)
     // index maps on the GPU
     h->d_jI.reserve((size_t)L.nnz_jac); h->d_jJ.reserve((size_t)L.nnz_jac);
     h->d_hI.reserve((size_t)L.nnz_h); h->d_hJ.reserve((size_t)L.nnz_h);
+    if (!h->ev_struct[0]) { CK(cudaEventCreate(&h->ev_struct[0])); CK(cudaEventCreate(&h->ev_struct[1])); }
+    CK(cudaEventRecord(h->ev_struct[0], h->stream));
     k_jac_structure<<<(unsigned)((L.nnz_jac + 255) / 256), 256, 0, h->stream>>>(L, T, h->d_jI.p, h->d_jJ.p);
     k_hess_structure<<<(unsigned)((L.nnz_h + 255) / 256), 256, 0, h->stream>>>(L, T, h->d_hI.p, h->d_hJ.p);
+    CK(cudaEventRecord(h->ev_struct[1], h->stream));
     h->launches += 2;
     CK(cudaGetLastError());
-    // host copy of the constant tail of the Jacobian values (LpNLPWrapper.cpp:242,:246-252,:715-718)
-    {
-        const size_t tail = (size_t)(L.nnz_jac - L.lin_val0);
-        h->h_ctail.assign(tail, 0.0);
-        for (int r = 0; r < P + Lp; ++r) { h->h_ctail[2 * r] = -1.0; h->h_ctail[2 * r + 1] = 1.0; }
-        if (L.ctot > 0) {
-            h->d_vals.reserve((size_t)L.nnz_jac);
-            h->launches += launch_fill_const(pd, h->stream, 1, h->d_vals.p);
-            CK(cudaMemcpyAsync(h->h_ctail.data() + (L.c0[0] - L.lin_val0), h->d_vals.p + L.c0[0], (size_t)L.ctot * sizeof(double),
-                               cudaMemcpyDeviceToHost, h->stream));
-        }
+    // the constant tail [L | C] of the Jacobian values lives in d_vals from here on; its host copy is made when a
+    // host-pointer Jacobian call first needs it (ensure_ctail): 160 MB at 100k nodes that device-pointer callers never touch
+    h->ctail_fresh = false;
+    if (L.ctot > 0) {
+        h->d_vals.reserve((size_t)L.nnz_jac);
+        h->launches += launch_fill_const(pd, h->stream, 1, h->d_vals.p);
     }
     // segment table of the head for the sparse return: every (row block, column block) of a phase's node
     // part is one maskable segment of N values; event rows and link entries are always returned
@@ -641,9 +643,33 @@ static void refresh(lpb_handle* h)
         CK(cudaMallocHost((void**)&h->h_seg_flags, (h->seg_off.size() + 1) * sizeof(int)));
     }
     CK(cudaStreamSynchronize(h->stream));
+    {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->ev_struct[0], h->ev_struct[1]) == cudaSuccess) h->structure_ns = (long long)(ms * 1e6);
+    }
     h->fresh = true;
     h->err_fresh = false;
     fast_path_drop(h);
+}
+
+// host copy of the constant tail of the Jacobian values (LpNLPWrapper.cpp:242,:246-252,:715-718): -1 / +1 of the
+// linear rows, then the differentiation-matrix entries as k_fill_const lays them out
+static void ensure_ctail(lpb_handle* h)
+{
+    if (h->ctail_fresh) return;
+    const Layout& L = h->lay;
+    const int P = (int)h->ph.size(), Lp = (int)h->lk.size();
+    const size_t tail = (size_t)(L.nnz_jac - L.lin_val0);
+    h->h_ctail.assign(tail, 0.0);
+    for (int r = 0; r < P + Lp; ++r) { h->h_ctail[2 * r] = -1.0; h->h_ctail[2 * r + 1] = 1.0; }
+    if (L.ctot > 0) {
+        h->d_vals.reserve((size_t)L.nnz_jac);
+        h->launches += launch_fill_const(h->pd, h->stream, 1, h->d_vals.p);
+        CK(cudaMemcpyAsync(h->h_ctail.data() + (L.c0[0] - L.lin_val0), h->d_vals.p + L.c0[0], (size_t)L.ctot * sizeof(double),
+                           cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    h->ctail_fresh = true;
 }
 
 // after the set of on-segments changed: device copy of the mask and the host's fill plan
@@ -1204,6 +1230,7 @@ int lpb_eval_g_jac_batch(lpb_handle* h, int nbatch, const double* x, double* g, 
     const bool sparse = values_dev && h->seg_mask_init && h->on_doubles * 4 <= head * 3;
     const bool flags_wanted = learn || sparse;
     std::vector<std::thread> th;
+    if (host_tail) ensure_ctail(h);
     bool in_place = false; // persistent_values: tail and fill patterns are still in the caller's array
     if (sparse && h->persistent_values && h->filled_values == values && h->filled_nbatch == nbatch && h->filled_plan == h->plan_version) {
         in_place = true;
@@ -1430,7 +1457,83 @@ int lpb_get_lgr_tables(lpb_handle* h, int phase, double* points, double* weights
 }
 
 // ---- mesh-error estimate and ph refinement --------------------------------------
-static void mesh_error_eval(lpb_handle* h, const double* x, std::vector<std::vector<double>>& rel, std::vector<std::vector<double>>& imax)
+// ---- relative error and its per-interval maximum on the GPU (round 1 did this on the host after copying both
+//      (M+1) x ns matrices back) ----
+// relative = absolute / (1 + column max of the interpolated state) (LpSolutionError.cpp:162-167); the reference's max
+// is `m = col[0]; for r: if (col[r] > m) m = col[r]`: NaNs after the first entry are skipped, a NaN first entry sticks.
+// One block per (state column, phase).
+__global__ void __launch_bounds__(256)
+k_err_colmax(const __grid_constant__ MeshErrDev me, int ns, const double* __restrict__ tem, double* __restrict__ colmax)
+{
+    __shared__ double red[256];
+    const int s = blockIdx.x, p = blockIdx.y;
+    const MeshErrPhase& mp = me.ph[p];
+    const int rows = mp.M + 1;
+    const double* __restrict__ col = tem + mp.out0 + (size_t)s * rows;
+    double m = -INFINITY;
+    for (int r = threadIdx.x; r < rows; r += blockDim.x) {
+        const double v = col[r];
+        m = v > m ? v : m;
+    }
+    red[threadIdx.x] = m;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (threadIdx.x < w) red[threadIdx.x] = red[threadIdx.x + w] > red[threadIdx.x] ? red[threadIdx.x + w] : red[threadIdx.x];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const double first = col[0];
+        colmax[p * ns + s] = (first != first) ? first : red[0];
+    }
+}
+
+// One block per mesh interval: rel = abs / (1 + colmax) on the interval's rows (its first new row .. the next
+// interval's first row, LpPhMeshRefineAlg.cpp:27-38) for every state, and the maximum of those (same NaN rule, the
+// first entry being state 0 at the interval's first row).
+__global__ void __launch_bounds__(64)
+k_err_relative(const __grid_constant__ MeshErrDev me, int P, int ns, const double* __restrict__ abs_err, const double* __restrict__ colmax,
+               double* __restrict__ rel, double* __restrict__ imax)
+{
+    __shared__ double red[64];
+    int p = 0, k = blockIdx.x;
+    while (p + 1 < P && k >= me.ph[p].K) { k -= me.ph[p].K; ++p; }
+    const MeshErrPhase& mp = me.ph[p];
+    const int rows = mp.M + 1, r0 = mp.int_rn0[k], cnt = mp.int_m[k] + 1;
+    double m = -INFINITY;
+    for (int e = threadIdx.x; e < cnt * ns; e += blockDim.x) {
+        const int s = e / cnt, r = r0 + (e - s * cnt);
+        const size_t at = (size_t)mp.out0 + (size_t)s * rows + r;
+        const double v = abs_err[at] / (1 + colmax[p * ns + s]);
+        rel[at] = v;
+        m = v > m ? v : m;
+    }
+    red[threadIdx.x] = m;
+    __syncthreads();
+    for (int w = 32; w > 0; w >>= 1) {
+        if (threadIdx.x < w) red[threadIdx.x] = red[threadIdx.x + w] > red[threadIdx.x] ? red[threadIdx.x + w] : red[threadIdx.x];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const double first = abs_err[(size_t)mp.out0 + r0] / (1 + colmax[p * ns]);
+        imax[blockIdx.x] = (first != first) ? first : red[0];
+    }
+}
+
+// both kernels; returns the launches made or a negative error
+static int launch_err_relative(cudaStream_t st, const MeshErrDev& me, int P, int ns, int total_intervals, const double* tem, const double* abs_err,
+                               double* colmax, double* rel, double* imax)
+{
+    k_err_colmax<<<dim3(ns, P), 256, 0, st>>>(me, ns, tem, colmax);
+    k_err_relative<<<total_intervals, 64, 0, st>>>(me, P, ns, abs_err, colmax, rel, imax);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 2 : cuda_fail(e);
+}
+
+// Mesh-error estimate of x, entirely on the GPU: k_mesh_error (interpolation, dae, integration defect), then the
+// relative error and its per-interval maximum (k_err_colmax, k_err_relative).  rel_out (sum over phases of
+// (M_p + 1) * ns doubles, phases concatenated, column-major) and imax_out (one per interval) are HOST destinations and
+// may be null: only what the caller asks for crosses PCIe.
+static void mesh_error_eval(lpb_handle* h, const double* x, double* rel_out, double* imax_out)
 {
     need_fresh(h);
     if (!x) throw ApiError(LPB_ERR_INVALID, "x is null");
@@ -1463,55 +1566,59 @@ static void mesh_error_eval(lpb_handle* h, const double* x, std::vector<std::vec
         nint += h->ph[ip].etab.K;
         for (int v : h->ph[ip].nodes) max_n = v > max_n ? v : max_n;
     }
+    h->d_colmax.reserve((size_t)P * ns);
+    h->d_rel.reserve(total);
+    h->d_imax.reserve((size_t)nint);
     h2d(h, h->d_x, x, (size_t)h->pd.n);
     note_launches(h, h->vt->mesh_error(h->pd, h->consts.data(), h->stream, h->med, nint, max_n, h->d_x.p, h->d_tem.p, h->d_abserr.p));
-    std::vector<double> tem(total), err(total);
-    CK(cudaMemcpyAsync(tem.data(), h->d_tem.p, total * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(err.data(), h->d_abserr.p, total * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    note_launches(h, launch_err_relative(h->stream, h->med, P, ns, nint, h->d_tem.p, h->d_abserr.p, h->d_colmax.p, h->d_rel.p, h->d_imax.p));
+    if (rel_out) CK(cudaMemcpyAsync(rel_out, h->d_rel.p, total * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (imax_out) CK(cudaMemcpyAsync(imax_out, h->d_imax.p, (size_t)nint * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    // relative error = absolute / (1 + column max of the interpolated state) (LpSolutionError.cpp:162-167) and
-    // its maximum over the rows of each interval (LpPhMeshRefineAlg.cpp:27-38): O(M ns) host arithmetic
-    rel.assign(P, {});
-    imax.assign(P, {});
-    size_t off = 0;
-    for (int ip = 0; ip < P; ++ip) {
+}
+
+// per-phase views of the flat results, for the refinement decisions
+static void mesh_error_split(lpb_handle* h, const std::vector<double>* rel_flat, const std::vector<double>& imax_flat,
+                             std::vector<std::vector<double>>* rel, std::vector<std::vector<double>>& imax)
+{
+    const int ns = h->vt->NS;
+    size_t kr = 0, ki = 0;
+    imax.assign(h->ph.size(), {});
+    if (rel) rel->assign(h->ph.size(), {});
+    for (size_t ip = 0; ip < h->ph.size(); ++ip) {
         const ErrTables& e = h->ph[ip].etab;
-        const int rows = e.M + 1;
-        rel[ip].assign((size_t)rows * ns, 0.0);
-        for (int s = 0; s < ns; ++s) {
-            const double* tcol = tem.data() + off + (size_t)s * rows;
-            double mx = tcol[0];
-            for (int r = 1; r < rows; ++r) mx = tcol[r] > mx ? tcol[r] : mx;
-            const double den = 1 + mx;
-            for (int r = 0; r < rows; ++r) rel[ip][(size_t)s * rows + r] = err[off + (size_t)s * rows + r] / den;
-        }
-        imax[ip].assign(e.K, 0.0);
-        for (int k = 0; k < e.K; ++k) {
-            double mx = rel[ip][e.int_rn0[k]];
-            for (int s = 0; s < ns; ++s)
-                for (int r = e.int_rn0[k]; r <= e.int_rn0[k] + e.int_m[k]; ++r) {
-                    const double v = rel[ip][(size_t)s * rows + r];
-                    mx = v > mx ? v : mx;
-                }
-            imax[ip][k] = mx;
-        }
-        off += (size_t)rows * ns;
+        const size_t nr = (size_t)(e.M + 1) * ns;
+        if (rel) (*rel)[ip].assign(rel_flat->begin() + kr, rel_flat->begin() + kr + nr);
+        imax[ip].assign(imax_flat.begin() + ki, imax_flat.begin() + ki + e.K);
+        kr += nr;
+        ki += e.K;
     }
+}
+
+static size_t mesh_error_sizes(lpb_handle* h, size_t* nint)
+{
+    size_t total = 0;
+    *nint = 0;
+    for (const PhaseHost& p : h->ph) {
+        size_t M = 0;
+        for (int v : p.nodes) M += (size_t)v + 1;
+        total += (M + 1) * (size_t)h->vt->NS;
+        *nint += p.nodes.size();
+    }
+    return total;
 }
 
 int lpb_mesh_error(lpb_handle* h, const double* x, int* rows_out, double* rel_err, double* interval_max)
 {
     LPB_API_BEGIN(h)
-    std::vector<std::vector<double>> rel, imax;
-    mesh_error_eval(h, x, rel, imax);
-    size_t kr = 0, ki = 0;
-    for (size_t ip = 0; ip < rel.size(); ++ip) {
-        if (rows_out) rows_out[ip] = h->ph[ip].etab.M + 1;
-        if (rel_err) std::memcpy(rel_err + kr, rel[ip].data(), rel[ip].size() * sizeof(double));
-        if (interval_max) std::memcpy(interval_max + ki, imax[ip].data(), imax[ip].size() * sizeof(double));
-        kr += rel[ip].size();
-        ki += imax[ip].size();
-    }
+    need_fresh(h);
+    if (rel_err || interval_max) mesh_error_eval(h, x, rel_err, interval_max); // both null: a sizing call, rows_out only
+    if (rows_out)
+        for (size_t ip = 0; ip < h->ph.size(); ++ip) {
+            int M = 0;
+            for (int v : h->ph[ip].nodes) M += v + 1;
+            rows_out[ip] = M + 1;
+        }
     LPB_API_END(h)
 }
 
@@ -1544,8 +1651,14 @@ int lpb_refine_mesh_ph(lpb_handle* h, const double* x, double tol, int Nmax, int
     LPB_API_BEGIN(h)
     if (!no_more_refine || !K_out || !mesh_out || !nodes_out) throw ApiError(LPB_ERR_INVALID, "null output");
     if (!(tol > 0) || Nmin < 2 || Nmax < Nmin) throw ApiError(LPB_ERR_INVALID, "bad refinement options");
-    std::vector<std::vector<double>> rel, imax;
-    mesh_error_eval(h, x, rel, imax);
+    std::vector<std::vector<double>> imax;
+    {
+        size_t nint = 0;
+        mesh_error_sizes(h, &nint);
+        std::vector<double> imax_flat(nint);
+        mesh_error_eval(h, x, nullptr, imax_flat.data()); // the ph decision reads the interval maxima only
+        mesh_error_split(h, nullptr, imax_flat, nullptr, imax);
+    }
     bool done = true;
     std::vector<std::vector<double>> meshes(h->ph.size());
     std::vector<std::vector<int>> counts(h->ph.size());
@@ -1594,7 +1707,12 @@ int lpb_refine_mesh_hp_liu(lpb_handle* h, const double* x, double tol, int Nmax,
     if (!no_more_refine || !K_out || !mesh_out || !nodes_out) throw ApiError(LPB_ERR_INVALID, "null output");
     if (!(tol > 0) || Nmax < 2 || !(ratio_R > 0)) throw ApiError(LPB_ERR_INVALID, "bad refinement options");
     std::vector<std::vector<double>> rel, imax;
-    mesh_error_eval(h, x, rel, imax); // GPU: interpolation to one more LGR point per interval, dae there, integration defect
+    {   // GPU: interpolation to one more LGR point per interval, dae there, integration defect, relative error
+        size_t nint = 0;
+        std::vector<double> rel_flat(mesh_error_sizes(h, &nint)), imax_flat(nint);
+        mesh_error_eval(h, x, rel_flat.data(), imax_flat.data());
+        mesh_error_split(h, &rel_flat, imax_flat, &rel, imax);
+    }
     const int ns = h->vt->NS, nc = h->vt->NC;
     std::vector<LiuPhaseInput> in(h->ph.size());
     for (size_t ip = 0; ip < h->ph.size(); ++ip) {
@@ -1762,6 +1880,7 @@ int lpb_get_stat(lpb_handle* h, const char* name, long long* value)
     else if (!std::strcmp(name, "sparse_on_doubles")) *value = h->seg_mask_init ? (long long)h->on_doubles : -1;
     else if (!std::strcmp(name, "head_doubles")) *value = (long long)h->pd.lin_val0;
     else if (!std::strcmp(name, "persistent_hits")) *value = h->persistent_hits;
+    else if (!std::strcmp(name, "structure_ns")) *value = h->structure_ns;
     else if (!std::strcmp(name, "fast_path_hits")) *value = h->fp.hits;
     else if (!std::strcmp(name, "fast_path_evals")) *value = h->fp.evals;
     else if (!std::strncmp(name, "hess_I0.", 8) || !std::strncmp(name, "hess_E0.", 8) || !std::strncmp(name, "hess_L0.", 8)) {

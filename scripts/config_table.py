@@ -17,6 +17,18 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
+def _hbm_peak():
+    """GB/s: the driver-measured copy bandwidth (MEASURED_PEAKS.json), else the profiling recipe's fallback."""
+    import json
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
+HBM_PEAK = _hbm_peak()
+
+
 def dev_ms(fn, reps):
     import torch
     for _ in range(3):
@@ -144,9 +156,11 @@ def main():
             # per-mesh and per-solve steps around the callbacks (host wall clock, one problem): index maps + tables
             # rebuilt on the GPU, NLP -> optimal-control conversion, mesh-error estimate
             ms_refresh = wall_ms(g.refresh, 3)
+            st_ms = g.get_stat("structure_ns") / 1e6            # k_jac_structure + k_hess_structure, CUDA events inside lpb_refresh
+            st_bytes = 8.0 * (nnz + g.get_nlp_info()[3])        # two 32-bit indices per triplet of both index maps
             ms_n2o = wall_ms(lambda: g.nlp2op(X[0], lam), 3)
             ms_err = wall_ms(lambda: g.mesh_error(X[0]), 3)
-            print("%-26s %9s %9s %10s | refresh (tables + index maps on the GPU) %.3f ms, nlp2op %.3f ms, mesh_error %.3f ms" % ("", "", "", "", ms_refresh, ms_n2o, ms_err), flush=True)
+            print("%-26s %9s %9s %10s | refresh (tables + index maps on the GPU) %.3f ms wall, of which the two index-map kernels %.3f ms = %.0f GB/s of 8 (nnz_jac + nnz_h) bytes (%.2f of the HBM peak); nlp2op %.3f ms, mesh_error %.3f ms (both with pageable host copies of x / lambda / results inside)" % ("", "", "", "", ms_refresh, st_ms, st_bytes / (st_ms * 1e-3) / 1e9 if st_ms > 0 else 0.0, st_bytes / (st_ms * 1e-3) / 1e9 / HBM_PEAK if st_ms > 0 else 0.0, ms_n2o, ms_err), flush=True)
         del g
 
 

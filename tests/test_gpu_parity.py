@@ -371,3 +371,25 @@ def test_tiled_hessian_kernel_is_bit_identical(nlp_mod, name, probe):
         h_g = g.eval_h(xx, sigma, lam)
         assert np.array_equal(h_t.view(np.int64), h_g.view(np.int64)), np.flatnonzero(h_t.view(np.int64) != h_g.view(np.int64))[:10]
     g.close()
+
+
+def test_nlp2op_end_rows_on_a_long_mesh(nlp_mod):
+    """The spline end rows of lpb_nlp2op on a mesh of 12 000 nodes: k_nlp2op_ends starts the forward sweep 512 knots
+    before the end (the sweep forgets its start geometrically); adaptive.natural_spline restates the reference's sweep
+    over ALL knots (LpGuessChecker.cpp:208-262, pinned to the reference in test_reference_pin.py) -- same values."""
+    from lpopc_b200 import adaptive, examples
+    op = examples.synthetic20(intervals=3000, nodes=4)
+    g = nlp_mod.TranscribedNLP(op)
+    n, m = g.get_nlp_info()[:2]
+    rng = np.random.Generator(np.random.PCG64(11))
+    x = g.initial_guess() + 1e-2 * rng.standard_normal(n)
+    lam = rng.standard_normal(m)
+    res, _ = g.nlp2op(x, lam)
+    tau = g.lgr_points()[0]
+    N, ns, nc = tau.size, len(op.phases[0].statemin), len(op.phases[0].controlmin)
+    assert N == 12000 and res[0]["control"].shape == (N + 1, nc)
+    for j in range(nc):
+        u = x[ns * (N + 1) + j * N: ns * (N + 1) + (j + 1) * N]
+        full = float(adaptive.natural_spline(tau, u, np.array([1.0]))[0])
+        assert abs(res[0]["control"][N, j] - full) <= RTOL * abs(full), j
+        assert np.array_equal(res[0]["control"][:N, j], u)
