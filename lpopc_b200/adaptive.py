@@ -100,7 +100,7 @@ def slsqp_host_solver(ftol=1e-10, maxiter=600):
 
 
 def solve_adaptive(op, make_nlp, make_evaluator, solver_cls, mesh_tol=1e-6, nmax=16, nmin=4, max_grids=10, ipm_tol=1e-6,
-                   max_iter=200, verbose=False, host_solver=None, method="ph", ratio_r=1.2):
+                   max_iter=200, verbose=False, host_solver=None, method="ph", ratio_r=1.2, max_nodes=None):
     """Runs the mesh loop on `op` (its phases' meshes are updated in place).
 
     make_nlp(op) -> object with lgr_points(), initial_guess(), set_mesh(), refresh(), probe_dependencies(),
@@ -108,7 +108,9 @@ def solve_adaptive(op, make_nlp, make_evaluator, solver_cls, mesh_tol=1e-6, nmax
     solver_cls (lpopc_b200.solver.CudaEvaluator / BatchedIPM).  host_solver(nlp, x) -> (x, obj, status, iters), if
     given, replaces the GPU-resident solver with a host outer loop on the TNLP callbacks (the reference's own
     arrangement: IPOPT on the host, `slsqp_host_solver()` here).  method = "ph" (PhMeshRefineAlg) or "hp-Liu"
-    (LiuHpMeshRefineAlg; option "mesh-refine-methods", LpMeshRefiner.h:44-61).  Returns (x, history)."""
+    (LiuHpMeshRefineAlg; option "mesh-refine-methods", LpMeshRefiner.h:44-61).  max_nodes: stop (record "node_cap") instead
+    of moving to a mesh with more LGR nodes in total than this -- a tolerance below the finite-difference noise floor
+    otherwise doubles the mesh until memory runs out.  Returns (x, history)."""
     nlp = make_nlp(op)
     if method == "hp-Liu":
         nlp.refine_reset()
@@ -144,6 +146,9 @@ def solve_adaptive(op, make_nlp, make_evaluator, solver_cls, mesh_tol=1e-6, nmax
             # interval whose error exceeds tol by less than a factor N is "refined" to itself; the reference would
             # repeat the identical solve until max-grid-num -- stop instead and say so
             rec["mesh_stalled"] = True
+            break
+        if max_nodes is not None and sum(int(np.sum(nd)) for _, nd in meshes) > max_nodes:
+            rec["node_cap"] = True
             break
         old_pts = nlp.lgr_points()
         # last control row of the converted solution (spline end rows, k_nlp2op_ends); multipliers do not enter it

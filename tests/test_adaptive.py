@@ -86,3 +86,23 @@ def test_adaptive_loop_brachistochrone_gpu_resident_solver():
     assert all(h["status"] == 0 for h in hist) and len(hist) >= 2
     assert hist[-1]["mesh_satisfied"] and hist[-1]["max_rel_error"] <= 1e-5 < hist[0]["max_rel_error"]
     assert abs(hist[-1]["objective"] - 0.824338669) <= 1e-7
+
+
+@pytest.mark.gpu
+def test_adaptive_loop_brachistochrone_to_two_thousand_nodes():
+    """BASELINE config 2: brachistochrone through the adaptive loop until the mesh holds ~2k LGR nodes.  The mesh tolerance
+    is set below what finite-difference derivatives can certify, so ph refinement keeps dividing (Nmax = 8, Nmin = 4) and
+    every grid means new sizes, new index maps on the GPU (lpb_set_mesh + lpb_refresh), a spline-transferred warm start
+    and a GPU-resident solve; max_nodes stops the loop at the first mesh beyond 2400 nodes."""
+    from lpopc_b200 import nlp, solver
+    op = examples.brachistochrone(intervals=40, nodes=6)
+    x, hist = adaptive.solve_adaptive(op, nlp.TranscribedNLP, solver.CudaEvaluator, solver.BatchedIPM, mesh_tol=1e-12, nmax=8, nmin=4,
+                                      max_grids=24, max_iter=300, max_nodes=2400)
+    assert hist[-1].get("node_cap") and not hist[-1]["mesh_satisfied"]
+    assert 1600 <= hist[-1]["nodes"][0] <= 2400, [h["nodes"] for h in hist]
+    assert all(h["status"] == 0 for h in hist)
+    sizes = [h["n"] for h in hist]
+    assert all(b > a for a, b in zip(sizes, sizes[1:]))            # every grid was a re-transcription to a larger NLP
+    assert all(abs(h["objective"] - 0.824338669) <= 2e-5 for h in hist)  # KKT tolerance 1e-6 per solve
+    assert hist[-1]["max_rel_error"] <= 1e-7
+    assert x.shape == (hist[-1]["n"],)
