@@ -617,8 +617,9 @@ def main():
                   "seconds_per_rank": [round(v, 3) for v in per_rank[:, 0].tolist()], "iters_max_per_rank": [int(v) for v in per_rank[:, 1].tolist()],
                   "solver": "lockstep primal-dual interior point, exact FD Hessian, KKT step: %s; block solves = lpb_blocktri_solve "
                             "(one launch per solve), factorisation = %s; NLP callbacks = device-resident transcription kernels"
-                            % (ipm.kkt_kind, "lpb_blocktri_factor for blocks <= 64 or <= 256 active instances, cuSOLVER batched Cholesky + cuBLAS otherwise"
-                               if getattr(ipm.kkt, "fused_factor", False) else "cuSOLVER batched Cholesky + cuBLAS")}
+                            % (ipm.kkt_kind, "lpb_kkt_factor (assembly incl. gamma J^T J, block Cholesky and inertia retry in one launch per iteration)"
+                               if getattr(ipm.kkt, "fused_factor", False) and not getattr(ipm.kkt, "_kkt_fused_off", False)
+                               else "cuSOLVER batched Cholesky + cuBLAS")}
         del g2, ev, ipm, res
 
     if rank == 0:
