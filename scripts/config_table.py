@@ -156,7 +156,7 @@ def main():
             # per-mesh and per-solve steps around the callbacks (host wall clock, one problem): index maps + tables
             # rebuilt on the GPU, NLP -> optimal-control conversion, mesh-error estimate
             ms_refresh = wall_ms(g.refresh, 3)
-            st_ms = g.get_stat("structure_ns") / 1e6            # k_jac_structure + k_hess_structure, CUDA events inside lpb_refresh
+            st_ms = g.stat("structure_ns") / 1e6            # k_jac_structure + k_hess_structure, CUDA events inside lpb_refresh
             st_bytes = 8.0 * (nnz + g.get_nlp_info()[3])        # two 32-bit indices per triplet of both index maps
             ms_n2o = wall_ms(lambda: g.nlp2op(X[0], lam), 3)
             ms_err = wall_ms(lambda: g.mesh_error(X[0]), 3)

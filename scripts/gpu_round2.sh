@@ -23,5 +23,11 @@ CMD4="python scripts/kernel_sweep.py synthetic20 1 --intervals 10000 --nodes 10 
 $CMD4 > gpurun_out/ks.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:k_cons_jac_rows -s 2 -c 1 -f -o gpurun_out/prof_rows $CMD4 > gpurun_out/ncu_rows.log 2>&1
 echo "ncu rows rc=$?"
+CMD5="python scripts/dev/kkt_probe.py 1024"
+$CMD5 > gpurun_out/kkt.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:k_kkt_factor -s 1 -c 1 -f -o gpurun_out/prof_kkt $CMD5 > gpurun_out/ncu_kkt.log 2>&1
+echo "ncu kkt rc=$?"
+python scripts/dev/solver_kernels.py 4096 > gpurun_out/solver_kernels.txt 2>&1; echo "solver kernels rc=$?"
+python scripts/dev/permesh_probe.py > gpurun_out/permesh.txt 2>&1; echo "permesh rc=$?"
 python scripts/config_table.py > gpurun_out/config_table.txt 2> gpurun_out/config_table.err; echo "config table rc=$?"
 ls -la gpurun_out | tail -20
