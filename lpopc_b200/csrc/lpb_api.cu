@@ -270,6 +270,7 @@ k_return_head(const __grid_constant__ SegDev sg, int nnz, const double* __restri
         bits = __reduce_or_sync(0xffffffffu, bits);
         if (lane == 0 && (sg.flags[s] & bits) != bits) atomicOr(sg.flags + s, bits);
     } else if (sg.on[s]) {
+        if (host_vals == nullptr) return; // return_mode 1: the copy engine moves the on-runs
         double* __restrict__ dst = host_vals + base;
         for (int i = lane; i < len; i += 32) dst[i] = __ldcs(src + i);
     } else {
@@ -404,6 +405,8 @@ struct lpb_handle {
     std::vector<long long> seg_fill; // bit pattern of an off segment (+0.0 or -0.0)
     struct FillRun { size_t off, len; long long bits; };
     std::vector<FillRun> fill_runs;
+    std::vector<FillRun> on_runs; // maximal runs of adjacent on-segments (return_mode 1: one strided DMA copy each)
+    int return_mode = 0;          // sparse return of the head: 0 = zero-copy stores of k_return_head, 1 = one cudaMemcpy2DAsync per on-run
     size_t on_doubles = 0;   // doubles per instance that cross PCIe on the sparse path
     DevBuf<int> d_seg_off, d_seg_len, d_seg_flags;
     DevBuf<long long> d_seg_fill;
@@ -677,12 +680,18 @@ static void rebuild_sparse_plan(lpb_handle* h)
 {
     const size_t nseg = h->seg_off.size();
     h->fill_runs.clear();
+    h->on_runs.clear();
     h->on_doubles = 0;
     ++h->plan_version; // whatever an earlier call left in a caller's array no longer matches the plan
     for (size_t s = 0; s < nseg; ++s) {
         if (!h->seg_maskable[s]) h->seg_on[s] = 1;
-        if (h->seg_on[s]) { h->on_doubles += (size_t)h->seg_len[s]; continue; }
         const size_t off = (size_t)h->seg_off[s], len = (size_t)h->seg_len[s];
+        if (h->seg_on[s]) {
+            h->on_doubles += len;
+            if (!h->on_runs.empty() && h->on_runs.back().off + h->on_runs.back().len == off) h->on_runs.back().len += len;
+            else h->on_runs.push_back({off, len, 0LL});
+            continue;
+        }
         if (!h->fill_runs.empty() && h->fill_runs.back().off + h->fill_runs.back().len == off && h->fill_runs.back().bits == h->seg_fill[s])
             h->fill_runs.back().len += len;
         else h->fill_runs.push_back({off, len, h->seg_fill[s]});
@@ -1181,7 +1190,7 @@ static void stream_fill(double* dst, size_t n, long long bits)
 #endif
 }
 
-static int launch_return_head(lpb_handle* h, cudaStream_t st, int nb, const double* d_vals, double* host_vals_dev)
+static int launch_return_head(lpb_handle* h, cudaStream_t st, int nb, const double* d_vals, double* host_vals_dev, bool verify_only = false)
 {
     SegDev sg;
     sg.off = h->d_seg_off.p; sg.len = h->d_seg_len.p; sg.on = h->d_seg_on.p; sg.fill = h->d_seg_fill.p; sg.flags = h->d_seg_flags.p;
@@ -1191,7 +1200,8 @@ static int launch_return_head(lpb_handle* h, cudaStream_t st, int nb, const doub
     for (int b0 = 0; b0 < nb; b0 += 65535) {
         const int cnt = nb - b0 < 65535 ? nb - b0 : 65535;
         const dim3 grid((unsigned)((sg.nseg + 7) / 8), (unsigned)cnt);
-        if (host_vals_dev) k_return_head<false><<<grid, 256, 0, st>>>(sg, h->pd.nnz_jac, d_vals + (size_t)b0 * nnz, host_vals_dev + (size_t)b0 * nnz);
+        if (verify_only) k_return_head<false><<<grid, 256, 0, st>>>(sg, h->pd.nnz_jac, d_vals + (size_t)b0 * nnz, nullptr);
+        else if (host_vals_dev) k_return_head<false><<<grid, 256, 0, st>>>(sg, h->pd.nnz_jac, d_vals + (size_t)b0 * nnz, host_vals_dev + (size_t)b0 * nnz);
         else k_return_head<true><<<grid, 256, 0, st>>>(sg, h->pd.nnz_jac, d_vals + (size_t)b0 * nnz, nullptr);
         ++launches;
     }
@@ -1267,6 +1277,7 @@ int lpb_eval_g_jac_batch(lpb_handle* h, int nbatch, const double* x, double* g, 
     // chunked pipeline over two streams: H2D of chunk c+1 and the kernels of chunk c overlap the
     // D2H of chunk c-1 (the D2H direction is the bottleneck of the whole call)
     int nchunk = nbatch >= 64 ? 8 : 1;
+    if (sparse && h->return_mode == 1 && nchunk > 2) nchunk = 2; // one copy per on-run and chunk: keep the count of copies down
     const int per = (nbatch + nchunk - 1) / nchunk;
     if (nchunk > 1 && !h->pipe[0]) {
         CK(cudaStreamCreateWithFlags(&h->pipe[0], cudaStreamNonBlocking));
@@ -1289,7 +1300,16 @@ int lpb_eval_g_jac_batch(lpb_handle* h, int nbatch, const double* x, double* g, 
             rc = lpb_eval_g_jac_dev(h, nb, h->d_x.p + (size_t)b0 * n, g ? h->d_g.p + (size_t)b0 * m : nullptr,
                                     values ? h->d_vals.p + (size_t)b0 * nnz : nullptr);
             if (rc != LPB_OK) { err = h->err; break; }
-            if (sparse && !(h->debug_skip & 2)) h->launches += launch_return_head(h, st, nb, h->d_vals.p + (size_t)b0 * nnz, values_dev + (size_t)b0 * nnz);
+            if (sparse && !(h->debug_skip & 2)) {
+                if (h->return_mode == 1) { // off-segments verified on the device, on-runs moved by the copy engine (strided rows)
+                    h->launches += launch_return_head(h, st, nb, h->d_vals.p + (size_t)b0 * nnz, nullptr, true);
+                    for (const lpb_handle::FillRun& r : h->on_runs)
+                        CK(cudaMemcpy2DAsync(values + (size_t)b0 * nnz + r.off, nnz * sizeof(double), h->d_vals.p + (size_t)b0 * nnz + r.off, nnz * sizeof(double),
+                                             r.len * sizeof(double), (size_t)nb, cudaMemcpyDeviceToHost, st));
+                } else {
+                    h->launches += launch_return_head(h, st, nb, h->d_vals.p + (size_t)b0 * nnz, values_dev + (size_t)b0 * nnz);
+                }
+            }
             if (g) CK(cudaMemcpyAsync(g + (size_t)b0 * m, h->d_g.p + (size_t)b0 * m, (size_t)nb * m * sizeof(double), cudaMemcpyDeviceToHost, st));
             if (values && !host_tail)
                 CK(cudaMemcpyAsync(values + (size_t)b0 * nnz, h->d_vals.p + (size_t)b0 * nnz, (size_t)nb * nnz * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -1848,6 +1868,7 @@ int lpb_set_option_int(lpb_handle* h, const char* name, int value)
     else if (!std::strcmp(name, "hess_variant")) h->opts.hess_variant = value;
     else if (!std::strcmp(name, "sweep_mode")) h->opts.sweep_mode = value;
     else if (!std::strcmp(name, "rotate_nodes")) h->opts.no_rotate = value ? 0 : 1;
+    else if (!std::strcmp(name, "return_mode")) h->return_mode = value ? 1 : 0;
     else if (!std::strcmp(name, "stage_values")) h->opts.stage_values = value;
     else if (!std::strcmp(name, "time_kernels")) h->time_kernels = value != 0;
     else throw ApiError(LPB_ERR_INVALID, std::string("unknown option ") + name);
