@@ -170,6 +170,17 @@ def test_fused_block_tridiagonal_solve_matches_library(B, K, nb, nbd):
     assert rc == 0
     torch.cuda.synchronize()
     assert float(((out2.cpu() - xref).abs().max() / xref.abs().max()).item()) <= 1e-11
+    # lpb_blocktri_solve_masked: instances whose mask byte is 0 are skipped (zero solution), the others are bit-identical
+    mask = torch.ones(B, dtype=torch.uint8, device=dev)
+    mask[B // 2] = 0
+    out3 = torch.full_like(rd, float("nan"))
+    rc = lib.lpb_blocktri_solve_masked(B, K, nb, nbd, Lp2, Cp2, K * nb * nb, max(K - 1, 1) * nbd * nb, C.c_void_p(bnd32.data_ptr()),
+                                       C.c_void_p(mask.data_ptr()), C.c_void_p(rd.data_ptr()), C.c_void_p(out3.data_ptr()),
+                                       C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0
+    torch.cuda.synchronize()
+    keep = mask.bool()
+    assert torch.equal(out3[keep], out2[keep]) and float(out3[~keep].abs().max()) == 0.0
     # an indefinite instance is reported (inertia test), the others are unaffected, everything stays finite
     if B >= 2:
         Dbad = Dd.clone()
