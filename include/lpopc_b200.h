@@ -226,6 +226,14 @@ int lpb_blocktri_solve_masked(int B, int K, int nb, int nbd, const double* const
                               long long strideC, const int* bnd, const unsigned char* active, const double* rhs, double* out,
                               void* cuda_stream);
 
+/* Batched sparse matrix-vector product y_b = A_b x_b (+ diag_b .* x_b) for matrices that share one CSR structure and
+ * take their values in place from per-instance triplet arrays: vals [B][val_stride], entry e of the CSR structure is
+ * vals[b][perm[e]].  The batched interior-point step multiplies with the Jacobian, its transpose and the Hessian this
+ * way (lpopc_b200/solver.py).  Device pointers; asynchronous on `stream`; returns 0, -1 (bad argument) or a negative
+ * cudaError_t - 1000.  No counterpart in the reference (IPOPT does this on the host). */
+int lpb_batched_spmv(int B, int nrows, int ncols, const int* rowptr, const int* col, const int* perm, const double* vals,
+                     long long val_stride, const double* x, const double* diag, double* y, void* stream);
+
 /* Tuning / introspection (not part of the reference boundary). */
 int lpb_set_option_int(lpb_handle* h, const char* name, int value);
 long long lpb_kernel_launch_count(const lpb_handle* h); /* kernels launched so far */

@@ -687,6 +687,37 @@ int launch_kkt_factor(const KktProblem& q, void* stream)
     return e == cudaSuccess ? 0 : -(int)e - 1000;
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_batched_spmv: y_b = A_b x_b for a batch of sparse matrices that share ONE structure (CSR: rowptr, col) and differ
+// in their values, which are read IN PLACE from the instance's triplet value array through perm (CSR position ->
+// triplet index): the Jacobian and Hessian values the transcription kernels wrote are used as they lie, no copy, no
+// dense block.  The KKT refinement of the batched interior-point step multiplies with J, J^T and H two to four times
+// per iteration; through dense blocks (cuBLAS gemv over [B][K][mr][nb + nbd]) that read 4 GB per product, the
+// triplets are 0.65 GB.  One CTA per instance, x in shared memory, one thread per row, entries added in CSR order:
+// deterministic, and consecutive rows (consecutive nodes of one state) read consecutive triplets.
+__global__ void __launch_bounds__(256)
+k_batched_spmv(int nrows, int ncols, const int* __restrict__ rowptr, const int* __restrict__ col, const int* __restrict__ perm,
+               const double* __restrict__ vals, long long val_stride, const double* __restrict__ x, const double* __restrict__ diag,
+               double* __restrict__ y, int x_in_smem)
+{
+    extern __shared__ double xs[];
+    const int b = blockIdx.x;
+    const double* __restrict__ xb = x + (size_t)b * ncols;
+    if (x_in_smem) {
+        for (int i = threadIdx.x; i < ncols; i += blockDim.x) xs[i] = xb[i];
+        __syncthreads();
+    }
+    const double* __restrict__ xv = x_in_smem ? xs : xb;
+    const double* __restrict__ vb = vals + (size_t)b * val_stride;
+    for (int r = threadIdx.x; r < nrows; r += blockDim.x) {
+        double acc = (diag != nullptr) ? diag[(size_t)b * nrows + r] * xv[r] : 0.0; // optional diagonal term (square matrices)
+        const int e1 = rowptr[r + 1];
+        for (int e = rowptr[r]; e < e1; ++e) acc += vb[perm[e]] * xv[col[e]];
+        y[(size_t)b * nrows + r] = acc;
+    }
+}
+
 } // namespace
 
 extern "C" {
@@ -764,6 +795,24 @@ int lpb_kkt_factor(int B, int K, int nb, int nbd, int mr, double gamma, const do
     int rc = launch_kkt_factor<8>(q, stream);
     if (rc == -1) rc = launch_kkt_factor<6>(q, stream);
     return rc;
+}
+
+// Batched sparse matrix-vector product with one shared structure (k_batched_spmv above).  rowptr [nrows + 1], col and
+// perm [rowptr[nrows]] on the device; vals [B][val_stride] (triplet values, addressed through perm); x [B][ncols];
+// diag [B][nrows] or null (adds diag_r x_r: nrows == ncols then); y [B][nrows].  Asynchronous on `stream`.
+int lpb_batched_spmv(int B, int nrows, int ncols, const int* rowptr, const int* col, const int* perm, const double* vals, long long val_stride,
+                     const double* x, const double* diag, double* y, void* stream)
+{
+    if (B < 1 || nrows < 1 || ncols < 1 || !rowptr || !col || !perm || !vals || !x || !y || (diag && nrows != ncols)) return -1;
+    const size_t shm = (size_t)ncols * sizeof(double);
+    const int in_smem = shm <= 160 * 1024 ? 1 : 0;
+    if (in_smem && shm > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_batched_spmv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
+        if (e != cudaSuccess) return -(int)e - 1000;
+    }
+    k_batched_spmv<<<B, 256, in_smem ? shm : 0, (cudaStream_t)stream>>>(nrows, ncols, rowptr, col, perm, vals, val_stride, x, diag, y, in_smem);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : -(int)e - 1000;
 }
 
 } // extern "C"

@@ -62,6 +62,7 @@ SIGNATURES = {
     "lpb_blocktri_solve_masked": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp), C.POINTER(_vp), C.c_longlong, C.c_longlong,
                                             _vp, _vp, _vp, _vp, _vp]),
     "lpb_blocktri_factor": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "lpb_batched_spmv": (C.c_int, [C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, C.c_longlong, _vp, _vp, _vp, _vp]),
     "lpb_kkt_factor": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lpb_nlp2op_length": (C.c_longlong, [_vp, C.POINTER(C.c_longlong)]),
     "lpb_nlp2op": (C.c_int, [_vp, _dp, _dp, _dp, _dp]),

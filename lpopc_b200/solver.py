@@ -317,6 +317,45 @@ class BlockTridiagKKT:
         real = torch.zeros(K * nb, dtype=torch.bool, device=dev)
         real[self.fpos] = True
         self.pad_diag = (~real).to(torch.float64).view(K, nb)  # 1 on padded slots (keeps the blocks non-singular)
+        # sparse products for the refinement (lpb_batched_spmv): J, J^T and H applied straight from the triplet values
+        # the transcription kernels wrote, in block-space indices (row slot dpos, column slot fpos) -- no dense block read
+        self._sp = None
+        if fused and dev.type == "cuda":
+            Rj, Cj = self.dpos[rr], self.fpos[c[sel]]
+            hi_, hj_ = self.fpos[hr[hs]], self.fpos[hc[hs]]
+            off_ = hi_ != hj_
+            self._sp = {"J": self._csr(Rj, Cj, sel, K * mr) + (K * mr, K * nb),
+                        "Jt": self._csr(Cj, Rj, sel, K * nb) + (K * nb, K * mr),
+                        "H": self._csr(torch.cat([hi_, hj_[off_]]), torch.cat([hj_, hi_[off_]]), torch.cat([hs, hs[off_]]), K * nb) + (K * nb, K * nb)}
+
+    @staticmethod
+    def _csr(rows, cols, perm, nrows):
+        """CSR structure (rowptr, col, perm as int32 device tensors) of the entries (rows, cols), in (row, perm) order."""
+        order = torch.argsort(rows * (int(perm.max().item()) + 1 if perm.numel() else 1) + perm)
+        counts = torch.bincount(rows[order], minlength=nrows)
+        rowptr = torch.zeros(nrows + 1, dtype=torch.int64, device=rows.device)
+        rowptr[1:] = torch.cumsum(counts, 0)
+        return (rowptr.to(torch.int32).contiguous(), cols[order].to(torch.int32).contiguous(), perm[order].to(torch.int32).contiguous())
+
+    def _spmv(self, which, vals, x, diag=None):
+        """y = A x (+ diag .* x) through lpb_batched_spmv; vals [B, nnz] triplet values, x [B, ncols] -> [B, nrows]."""
+        import ctypes as C
+        rowptr, col, perm, nrows, ncols = self._sp[which]
+        if getattr(self, "_lib", None) is None:
+            from . import nlp
+            self._lib = nlp.load_library()
+        B = x.shape[0]
+        x = x.reshape(B, ncols).contiguous()
+        vals = vals if vals.is_contiguous() else vals.contiguous()
+        y = torch.empty((B, nrows), dtype=torch.float64, device=x.device)
+        dg = None if diag is None else diag.reshape(B, nrows).contiguous()
+        rc = self._lib.lpb_batched_spmv(B, nrows, ncols, C.c_void_p(rowptr.data_ptr()), C.c_void_p(col.data_ptr()), C.c_void_p(perm.data_ptr()),
+                                        C.c_void_p(vals.data_ptr()), vals.stride(0), C.c_void_p(x.data_ptr()),
+                                        C.c_void_p(dg.data_ptr() if dg is not None else None), C.c_void_p(y.data_ptr()),
+                                        C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        if rc != 0:
+            raise RuntimeError("lpb_batched_spmv failed: %d" % rc)
+        return y
 
     # layout conversions
     def to_blocks(self, v):    # [B, nf] -> [B, K, nb]
@@ -340,15 +379,20 @@ class BlockTridiagKKT:
         Jb = torch.zeros((B, self.K * self.mr * self.ncol), dtype=torch.float64, device=jv.device)
         Jb.index_add_(1, self.j_flat, jv[:, self.j_sel])
         self.Jb = Jb.view(B, self.K, self.mr, self.ncol)
+        self.jv = jv  # triplet values as the kernels wrote them: the sparse products read them in place
 
     def _next_bnd(self, xb):   # [B, K, nb] -> boundary slots of the following block [B, K, nbd] (zeros after the last)
         nxt = xb[:, 1:, self.bnd]
         return torch.cat([nxt, torch.zeros_like(nxt[:, :1])], 1) if self.K > 1 else torch.zeros_like(xb[:, :, self.bnd])
 
     def _Jmul(self, xb):       # [B, K, nb] -> [B, K, mr]
+        if self._sp is not None and xb.is_cuda:
+            return self._spmv("J", self.jv, xb).view(-1, self.K, self.mr)
         return torch.einsum("bkmn,bkn->bkm", self.Jb, torch.cat([xb, self._next_bnd(xb)], 2))
 
     def _Jtmul(self, vb):      # [B, K, mr] -> [B, K, nb]
+        if self._sp is not None and vb.is_cuda:
+            return self._spmv("Jt", self.jv, vb).view(-1, self.K, self.nb)
         y = torch.einsum("bkmn,bkm->bkn", self.Jb, vb)
         out = y[:, :, :self.nb].clone()
         if self.K > 1:
@@ -356,6 +400,8 @@ class BlockTridiagKKT:
         return out
 
     def _Jtmul2(self, va, vb):  # J^T va and J^T vb in one sweep over the Jacobian blocks
+        if self._sp is not None and va.is_cuda:
+            return self._Jtmul(va), self._Jtmul(vb)
         y = torch.einsum("bkmn,bkmr->bknr", self.Jb, torch.stack([va, vb], 3))
         out = y[:, :, :self.nb].clone()
         if self.K > 1:
@@ -567,6 +613,8 @@ class BlockTridiagKKT:
         D[:, :, di, di] = base + dw.view(-1, 1, 1)  # H = W + Sigma + dw I (exact system of the refinement)
         r1b, cb = self.to_blocks(rhs1), self.dual_to_blocks(c)
         active = (~done).to(torch.uint8).contiguous()
+        # H = W + Sigma + dw I (+ 1 on padded slots): the triplets carry W, the rest is a diagonal
+        hdiag = (self.to_blocks(Sigma) + self.pad_diag + dw.view(-1, 1, 1)) if (self._sp is not None and hv.is_cuda) else None
         # iterative refinement on  [H J^T; J 0] [dx; dl] = -[r1; c].  H dx, J dx and J^T dl are carried along as running
         # sums of the products with the corrections (linear in them), so a pass costs one H product and two sweeps over
         # the dense Jacobian blocks (J ddx, and J^T [ddl, res2] in one) instead of one H product and four sweeps
@@ -589,7 +637,7 @@ class BlockTridiagKKT:
             dxb = dxb + ddx
             dlb = dlb + ddl
             if it < self.refine:
-                Hdx = Hdx + self._Hmul(D, E, ddx)
+                Hdx = Hdx + (self._spmv("H", hv, ddx, hdiag).view(B, K, nb) if hdiag is not None else self._Hmul(D, E, ddx))
                 Jdx = Jdx + Jddx
                 res2 = -cb - Jdx
                 Jt_ddl, Jt_res2 = self._Jtmul2(ddl, res2)

@@ -276,3 +276,46 @@ def test_kkt_factor_kernel_matches_library_assembly(B, K, nb, nbd, mr):
     for i in range(K - 1):
         assert float((Cf[i][live] - Cr[i][live]).abs().max() / Cr[i][live].abs().max().clamp(min=1e-300)) <= 1e-9, i
         assert float(Cf[i][0].abs().max()) == 0.0
+
+
+@pytest.mark.gpu
+def test_batched_spmv_matches_dense_products():
+    """lpb_batched_spmv (shared CSR structure, values read in place from per-instance triplet arrays through perm, with
+    duplicates and an optional diagonal term) against dense matrix-vector products assembled from the same triplets."""
+    import ctypes as C
+    from lpopc_b200 import nlp
+    lib = nlp.load_library()
+    dev = torch.device("cuda")
+    gen = torch.Generator(device="cpu").manual_seed(5)
+    B, nrows, ncols, nnz = 7, 53, 41, 400
+    rows = torch.randint(0, nrows, (nnz,), generator=gen)
+    cols = torch.randint(0, ncols, (nnz,), generator=gen)
+    rows[:ncols] = torch.arange(ncols) % nrows   # some structure, duplicates included by chance
+    vals = torch.randn(B, nnz + 9, generator=gen, dtype=torch.float64)  # stride > nnz: values sit inside a longer array
+    x = torch.randn(B, ncols, generator=gen, dtype=torch.float64)
+    dense = torch.zeros(B, nrows, ncols, dtype=torch.float64)
+    dense.index_put_((torch.arange(B).unsqueeze(1).expand(B, nnz), rows.expand(B, nnz), cols.expand(B, nnz)), vals[:, :nnz], accumulate=True)
+    rowptr, col, perm = solver.BlockTridiagKKT._csr(rows.to(dev), cols.to(dev), torch.arange(nnz, device=dev), nrows)
+    vd, xd = vals.to(dev), x.to(dev)
+    y = torch.empty(B, nrows, dtype=torch.float64, device=dev)
+    rc = lib.lpb_batched_spmv(B, nrows, ncols, C.c_void_p(rowptr.data_ptr()), C.c_void_p(col.data_ptr()), C.c_void_p(perm.data_ptr()),
+                              C.c_void_p(vd.data_ptr()), vd.stride(0), C.c_void_p(xd.data_ptr()), None, C.c_void_p(y.data_ptr()),
+                              C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0
+    ref = torch.einsum("bij,bj->bi", dense, x)
+    assert float((y.cpu() - ref).abs().max()) <= 1e-12 * float(ref.abs().max())
+    # square matrix with the diagonal term
+    n = 41
+    rows2 = torch.randint(0, n, (nnz,), generator=gen)
+    dg = torch.randn(B, n, generator=gen, dtype=torch.float64)
+    dense2 = torch.zeros(B, n, n, dtype=torch.float64)
+    dense2.index_put_((torch.arange(B).unsqueeze(1).expand(B, nnz), rows2.expand(B, nnz), cols.expand(B, nnz)), vals[:, :nnz], accumulate=True)
+    rowptr2, col2, perm2 = solver.BlockTridiagKKT._csr(rows2.to(dev), cols.to(dev), torch.arange(nnz, device=dev), n)
+    dgd = dg.to(dev)
+    y2 = torch.empty(B, n, dtype=torch.float64, device=dev)
+    rc = lib.lpb_batched_spmv(B, n, n, C.c_void_p(rowptr2.data_ptr()), C.c_void_p(col2.data_ptr()), C.c_void_p(perm2.data_ptr()),
+                              C.c_void_p(vd.data_ptr()), vd.stride(0), C.c_void_p(xd.data_ptr()), C.c_void_p(dgd.data_ptr()), C.c_void_p(y2.data_ptr()),
+                              C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0
+    ref2 = torch.einsum("bij,bj->bi", dense2, x) + dg * x
+    assert float((y2.cpu() - ref2).abs().max()) <= 1e-12 * float(ref2.abs().max())
