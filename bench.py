@@ -591,7 +591,7 @@ def main():
         ipm = solver.BatchedIPM(ev, tol=1e-6, max_iter=150, var_blocks=solver.interval_blocks(op, ev.n))
         ipm.solve(X0[:8], XL[:8], XU[:8])  # warm-up
         barrier()
-        solve_sampler = ClockSampler(local_rank, period_s=0.005)  # back-to-back polling would steal the GIL from the solver's Python loop
+        solve_sampler = ClockSampler(local_rank, period_s=0.015)  # back-to-back polling would steal the GIL from the solver's Python loop
         solve_sampler.start()
         ts = time.perf_counter()
         _prof = None

@@ -181,8 +181,8 @@ class DenseKKT:
         # drives its own regularisation dw (raised only for genuine negative curvature).
         JtJ = torch.bmm(J.transpose(1, 2), J)
         rhs1 = rhs1 + rho * self.Jt(c)
-        dw = torch.where(dw_last > 0, dw_last / 3.0, torch.zeros_like(dw_last))
-        dw = torch.where(dw < 1e-9, torch.zeros_like(dw), dw)
+        dw = torch.where(dw_last > 0, dw_last / 3.0, 0.0)
+        dw = torch.where(dw < 1e-9, 0.0, dw)
         Hd = W + rho * JtJ
         diag = torch.arange(nf, device=dev)
         base_diag = Hd[:, diag, diag] + Sigma
@@ -192,7 +192,7 @@ class DenseKKT:
             bad = (info != 0) & (~done)
             if not bool(bad.any()):
                 break
-            dw = torch.where(bad, torch.where(dw == 0, torch.full_like(dw, 1e-4), dw * (100.0 if _try < 2 else 8.0)), dw)
+            dw = torch.where(bad, torch.where(dw == 0, 1e-4, dw * (100.0 if _try < 2 else 8.0)), dw)
         not_pd = (info != 0) & (~done)  # still indefinite after the last try: the step of such an instance is not trusted (status 2)
         # condensed system of [H J^T; J 0][dx; dlam] = -[rhs1; c] with H = L L^T:
         #   Y = L^-1 J^T, y = L^-1 rhs1, S = Y^T Y, S dlam = c - Y^T y, dx = -L^-T (y + Y dlam)
@@ -205,7 +205,7 @@ class DenseKKT:
         bad_s = (info_s != 0) & (~done)
         failed = torch.zeros_like(done)
         if bool(bad_s.any()):  # rank-deficient Jacobian: regularise the (2,2) block harder
-            S[:, dS, dS] += torch.where(bad_s, 1e-8, 0.0).unsqueeze(1)
+            S[:, dS, dS] += (bad_s.to(torch.float64) * 1e-8).unsqueeze(1)
             Ls, info_s = blocked_cholesky_ex(S)
             failed = (info_s != 0) & (~done)
         failed = failed | not_pd
@@ -264,7 +264,7 @@ class BlockTridiagKKT:
         rmin = big.scatter_reduce(0, rr, cb, reduce="amin")
         rmax = torch.full((me,), -1, dtype=torch.int64, device=dev).scatter_reduce(0, rr, cb, reduce="amax")
         empty = rmax < 0
-        rmin = torch.where(empty, torch.zeros_like(rmin), rmin)
+        rmin = torch.where(empty, 0, rmin)
         if bool(((rmax - rmin) > 1).any()):
             raise ValueError("a constraint row couples non-adjacent blocks")
         rorder = torch.argsort(rmin * me + torch.arange(me, device=dev))
@@ -552,7 +552,7 @@ class BlockTridiagKKT:
             bad = (info != 0) & (~done)
             if not bool(bad.any()):
                 break
-            dw = torch.where(bad, torch.where(dw == 0, torch.full_like(dw, 1e-4), dw * (100.0 if _try < 2 else 8.0)), dw)
+            dw = torch.where(bad, torch.where(dw == 0, 1e-4, dw * (100.0 if _try < 2 else 8.0)), dw)
         return Ls, Cs, info, dw
 
     def _kkt_factor_fused(self, D, E, diag_add, dw0, done):
@@ -603,8 +603,8 @@ class BlockTridiagKKT:
         E = E.view(B, max(K - 1, 1), nbd, nb)
         di = torch.arange(nb, device=dev)
         base = D[:, :, di, di] + self.to_blocks(Sigma) + self.pad_diag
-        dw = torch.where(dw_last > 0, dw_last / 3.0, torch.zeros_like(dw_last))
-        dw = torch.where(dw < 1e-9, torch.zeros_like(dw), dw)
+        dw = torch.where(dw_last > 0, dw_last / 3.0, 0.0)
+        dw = torch.where(dw < 1e-9, 0.0, dw)
         fused = self._kkt_factor_fused(D, E, base - D[:, :, di, di], dw, done) if self.fused_factor else None
         if fused is not None:
             Ls, Cs, info, dw = fused
@@ -774,16 +774,16 @@ class BatchedIPM:
         sy = (sk * yk).sum(1)
         ss = (sk * sk).sum(1)
         yy = (yk * yk).sum(1)
-        delta = torch.where(sy > 0, yy / sy.clamp(min=1e-300), torch.ones_like(sy))
+        delta = torch.where(sy > 0, yy / sy.clamp(min=1e-300), 1.0)
         # Powell damping: y <- theta y + (1 - theta) delta s when s'y < 0.2 delta s's
-        th = torch.where(sy < 0.2 * delta * ss, 0.8 * delta * ss / (delta * ss - sy).clamp(min=1e-300), torch.ones_like(sy))
+        th = torch.where(sy < 0.2 * delta * ss, 0.8 * delta * ss / (delta * ss - sy).clamp(min=1e-300), 1.0)
         yk = th.unsqueeze(1) * yk + (1 - th).unsqueeze(1) * delta.unsqueeze(1) * sk
         use = active & (ss > 1e-24) & torch.isfinite(yk).all(1)
         M = S.shape[1]
         full = cnt >= M
         S = torch.where((use & full).view(-1, 1, 1), torch.roll(S, -1, 1), S)
         Y = torch.where((use & full).view(-1, 1, 1), torch.roll(Y, -1, 1), Y)
-        slot = torch.where(full, torch.full_like(cnt, M - 1), cnt)
+        slot = torch.where(full, M - 1, cnt)
         rows = torch.nonzero(use).squeeze(1)
         S[rows, slot[rows]] = sk[rows]
         Y[rows, slot[rows]] = yk[rows]
@@ -801,7 +801,7 @@ class BatchedIPM:
         rows = torch.arange(B, device=dev)
         sy_last = (S[rows, last] * Y[rows, last]).sum(1)
         yy_last = (Y[rows, last] * Y[rows, last]).sum(1)
-        delta = torch.where((cnt > 0) & (sy_last > 0), yy_last / sy_last.clamp(min=1e-300), torch.ones_like(sy_last))
+        delta = torch.where((cnt > 0) & (sy_last > 0), yy_last / sy_last.clamp(min=1e-300), 1.0)
         SY = torch.bmm(S, Y.transpose(1, 2))                      # s_i' y_j
         L = torch.tril(SY, diagonal=-1)
         D = torch.diagonal(SY, dim1=1, dim2=2)
@@ -878,8 +878,8 @@ class BatchedIPM:
             xf = torch.where(~hasL & hasU, torch.minimum(xf, hi - 1e-2 * torch.clamp(hi.abs(), min=1.0)), xf)
             X[:, F] = xf
             lam = torch.zeros((B, self.m), dtype=torch.float64, device=X.device)
-            zL = torch.where(hasL, torch.ones_like(lo), torch.zeros_like(lo))
-            zU = torch.where(hasU, torch.ones_like(hi), torch.zeros_like(hi))
+            zL = hasL.to(torch.float64)
+            zU = hasU.to(torch.float64)
             mu = torch.full((B,), self.mu0, dtype=torch.float64, device=X.device)
             nu = torch.full((B,), 1.0, dtype=torch.float64, device=X.device)  # l1 penalty
             dw_last = torch.zeros(B, dtype=torch.float64, device=X.device)
@@ -898,14 +898,14 @@ class BatchedIPM:
         sigma1 = torch.ones(B, dtype=torch.float64, device=X.device)
         kkt0 = torch.full((B,), float("inf"), dtype=torch.float64, device=X.device)
         inf = float("inf")
-        sl = lambda x: torch.where(hasL, x - lo, torch.ones_like(x))  # noqa: E731
-        su = lambda x: torch.where(hasU, hi - x, torch.ones_like(x))  # noqa: E731
+        sl = lambda x: torch.where(hasL, x - lo, 1.0)  # noqa: E731
+        su = lambda x: torch.where(hasU, hi - x, 1.0)  # noqa: E731
 
         def barrier_obj(Xt, mu_):
             xt = Xt[:, F]
             phi = ev.f(Xt)
-            phi = phi - mu_ * (torch.where(hasL, torch.log(sl(xt)), torch.zeros_like(xt)).sum(1)
-                               + torch.where(hasU, torch.log(su(xt)), torch.zeros_like(xt)).sum(1))
+            phi = phi - mu_ * (torch.where(hasL, torch.log(sl(xt)), 0.0).sum(1)
+                               + torch.where(hasU, torch.log(su(xt)), 0.0).sum(1))
             c = ev.g(Xt)[:, self.eq] - self.c_target
             return phi, c.abs().sum(1)
 
@@ -942,8 +942,8 @@ class BatchedIPM:
                 x_prev, gradf_prev = xf.clone(), gradf.clone()
                 Jprev = kkt.J.clone()
                 kkt_Jt_prev = lambda v, Jp=Jprev: torch.bmm(Jp.transpose(1, 2), v.unsqueeze(2)).squeeze(2)  # noqa: E731
-            compL = torch.where(hasL, sL * zL, torch.zeros_like(sL))
-            compU = torch.where(hasU, sU * zU, torch.zeros_like(sU))
+            compL = torch.where(hasL, sL * zL, 0.0)
+            compU = torch.where(hasU, sU * zU, 0.0)
             # scaled optimality error (IPOPT eq. (5)-(6)), smax = 100
             nz = (hasL.sum(1) + hasU.sum(1)).clamp(min=1)
             s_d = torch.clamp((lam_eq.abs().sum(1) + zL.sum(1) + zU.sum(1)) / (me + nz), min=100.0) / 100.0
@@ -977,33 +977,33 @@ class BatchedIPM:
                     break
                 mu = torch.where(upd, torch.clamp(torch.minimum(0.2 * mu, mu ** 1.5), min=self.tol / 10.0), mu)
                 # a new barrier problem: its filter starts empty (the objective phi_mu changed)
-                f_th = torch.where(upd.unsqueeze(1), torch.full_like(f_th, float("inf")), f_th)
-                f_ph = torch.where(upd.unsqueeze(1), torch.full_like(f_ph, float("inf")), f_ph)
-                f_n = torch.where(upd, torch.zeros_like(f_n), f_n)
+                f_th = torch.where(upd.unsqueeze(1), float("inf"), f_th)
+                f_ph = torch.where(upd.unsqueeze(1), float("inf"), f_ph)
+                f_n = torch.where(upd, 0, f_n)
             mu_c = mu.unsqueeze(1)
             # Hessian of the Lagrangian (exact, finite differences of the reference scheme) + Sigma
             if self.hessian == "limited-memory":
                 hv = self._lbfgs_matrix(lb_S, lb_Y, lb_n)
             else:
                 hv = ev.hess(X, sigma1, lam)
-            Sigma = torch.where(hasL, zL / sL, torch.zeros_like(sL)) + torch.where(hasU, zU / sU, torch.zeros_like(sU))
-            rhs1 = gradf + Jtlam - torch.where(hasL, mu_c / sL, torch.zeros_like(sL)) + torch.where(hasU, mu_c / sU, torch.zeros_like(sU))
+            Sigma = torch.where(hasL, zL / sL, 0.0) + torch.where(hasU, zU / sU, 0.0)
+            rhs1 = gradf + Jtlam - torch.where(hasL, mu_c / sL, 0.0) + torch.where(hasU, mu_c / sU, 0.0)
             dx, dlam, dw, kfail = kkt.step(hv, Sigma, rhs1, c, dw_last, done)
             failed |= kfail
             dw_last = torch.where(done, dw_last, dw)
-            dzL = torch.where(hasL, mu_c / sL - zL - zL / sL * dx, torch.zeros_like(dx))
-            dzU = torch.where(hasU, mu_c / sU - zU + zU / sU * dx, torch.zeros_like(dx))
+            dzL = torch.where(hasL, mu_c / sL - zL - zL / sL * dx, 0.0)
+            dzU = torch.where(hasU, mu_c / sU - zU + zU / sU * dx, 0.0)
             # fraction to the boundary
             tau = torch.clamp(1.0 - mu, min=0.99).unsqueeze(1)
             ratio = torch.full_like(dx, inf)
             ratio = torch.where(hasL & (dx < 0), -tau * sL / dx, ratio)
-            ratio = torch.minimum(ratio, torch.where(hasU & (dx > 0), tau * sU / dx, torch.full_like(dx, inf)))
+            ratio = torch.minimum(ratio, torch.where(hasU & (dx > 0), tau * sU / dx, inf))
             a_max = torch.clamp(ratio.amin(1), max=1.0)
             rz = torch.full_like(dx, inf)
             rz = torch.where(hasL & (dzL < 0), -tau * zL / dzL, rz)
-            rz = torch.minimum(rz, torch.where(hasU & (dzU < 0), -tau * zU / dzU, torch.full_like(dx, inf)))
+            rz = torch.minimum(rz, torch.where(hasU & (dzU < 0), -tau * zU / dzU, inf))
             a_z = torch.clamp(rz.amin(1), max=1.0)
-            gphi = gradf - torch.where(hasL, mu_c / sL, torch.zeros_like(sL)) + torch.where(hasU, mu_c / sU, torch.zeros_like(sU))
+            gphi = gradf - torch.where(hasL, mu_c / sL, 0.0) + torch.where(hasU, mu_c / sU, 0.0)
             c1 = c.abs().sum(1)
             gd = (gphi * dx).sum(1)
             phi0, _ = barrier_obj(X, mu)
@@ -1017,8 +1017,8 @@ class BatchedIPM:
                 th_max = 1e4 * torch.clamp(c1, min=1.0)
                 init = first | (f_n == 0)  # an empty filter only bounds the constraint violation
                 f_th[:, 0] = torch.where(init, th_max, f_th[:, 0])
-                f_ph[:, 0] = torch.where(init, torch.full_like(phi0, -float("inf")), f_ph[:, 0])
-                f_n = torch.where(init, torch.ones_like(f_n), f_n)
+                f_ph[:, 0] = torch.where(init, -float("inf"), f_ph[:, 0])
+                f_n = torch.where(init, 1, f_n)
                 ftype = torch.zeros_like(done)
                 a_min_ls = 1e-9
                 for _ls in range(40):
@@ -1044,11 +1044,11 @@ class BatchedIPM:
                 # accepted h-type steps (and f-type steps that did not satisfy Armijo) augment the filter
                 aug = accepted & ~done & ~ftype
                 if bool(aug.any()):
-                    slot = torch.where(f_n < self.filter_slots, f_n, torch.ones_like(f_n))  # full: overwrite from slot 1 on (slot 0 = bound)
+                    slot = torch.where(f_n < self.filter_slots, f_n, 1)  # full: overwrite from slot 1 on (slot 0 = bound)
                     rows = torch.nonzero(aug).squeeze(1)
                     f_th[rows, slot[rows]] = ((1 - g_th) * c1)[rows]
                     f_ph[rows, slot[rows]] = (phi0 - g_ph * c1)[rows]
-                    f_n = torch.where(aug, torch.where(f_n < self.filter_slots, f_n + 1, torch.full_like(f_n, 2)), f_n)
+                    f_n = torch.where(aug, torch.where(f_n < self.filter_slots, f_n + 1, 2), f_n)
             else:
                 # l1 merit: phi_mu(x) + nu |c|_1, Armijo backtracking
                 lam_new_inf = (lam_eq + dlam).abs().amax(1)
@@ -1074,9 +1074,9 @@ class BatchedIPM:
                 Xn[stuck] = Xt[stuck]
                 dw_last = torch.where(stuck, torch.clamp(dw_last * 100.0, min=1e-2), dw_last)
                 if self.linesearch == "filter":  # restart the filter of a stuck instance
-                    f_th = torch.where(stuck.unsqueeze(1), torch.full_like(f_th, float("inf")), f_th)
-                    f_ph = torch.where(stuck.unsqueeze(1), torch.full_like(f_ph, float("inf")), f_ph)
-                    f_n = torch.where(stuck, torch.zeros_like(f_n), f_n)
+                    f_th = torch.where(stuck.unsqueeze(1), float("inf"), f_th)
+                    f_ph = torch.where(stuck.unsqueeze(1), float("inf"), f_ph)
+                    f_n = torch.where(stuck, 0, f_n)
             self._last_alpha = alpha
             act = (~done).unsqueeze(1)
             a_col = alpha.unsqueeze(1)
@@ -1094,6 +1094,6 @@ class BatchedIPM:
             zU = torch.where(hasU, torch.maximum(torch.minimum(zU, 1e10 * mu_c / sU2), mu_c / (1e10 * sU2)), zU)
             iters += (~done).to(torch.int64)
         obj = ev.f(X)
-        status = torch.where(done, torch.zeros_like(iters), torch.ones_like(iters))
-        status = torch.where(failed & ~done, torch.full_like(iters, 2), status)
+        status = torch.where(done, 0, 1)
+        status = torch.where(failed & ~done, 2, status)
         return {"x": X, "obj": obj, "status": status, "iters": iters, "kkt_error": kkt0, "lam": lam, "state": suspended}
