@@ -12,6 +12,8 @@
 // lockstep iteration).  Here ONE launch does the whole solve: one CTA per instance, thread i owns row i of the
 // right-hand side, 32-row panels eliminated with register shuffles and one barrier per panel.
 #include <cuda_runtime.h>
+#include <mutex>
+#include <vector>
 #include <cstddef>
 #include <cstdint>
 
@@ -638,6 +640,100 @@ k_kkt_factor(const __grid_constant__ KktFactorArgs<T> a)
     }
 }
 
+// Packing of the block columns (NBR - J tiles each) into warps of 32 lanes.  A warp executes the trailing update of
+// step kb as long as ANY of its columns has J > kb, so what the packing costs is sum over warps of min(max J, NBA)
+// warp-steps.  First fit by decreasing length pairs the longest column with a short, LATE one and keeps that warp busy
+// at a third of its lanes (91 warp-steps for 21 columns on 8 warps); steepest descent over single moves and swaps
+// (ties broken towards columns of similar J sharing a warp) brings it to 73, the update phase's instruction count with it.
+// Results are cached per shape.  false: more than max_warps warps needed.
+static bool pack_columns(int NBR, int NBA, int max_warps, unsigned char* tI, unsigned char* tJ, int* nwarps_out)
+{
+    struct Packing { int NBR, NBA, max_warps, nwarps; unsigned char bin[32]; };
+    static std::mutex mu;
+    static std::vector<Packing> cache;
+    Packing pk{NBR, NBA, max_warps, 0, {0}};
+    bool found = false;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        for (const Packing& c : cache)
+            if (c.NBR == NBR && c.NBA == NBA && c.max_warps == max_warps) { pk = c; found = true; break; }
+    }
+    if (!found) {
+        int fill[32] = {0}, nb = 0;
+        for (int J = 0; J < NBR; ++J) { // first fit, longest first
+            const int len = NBR - J;
+            int w = 0;
+            while (w < nb && fill[w] + len > 32) ++w;
+            if (w == nb) {
+                if (nb == max_warps) return false;
+                ++nb;
+            }
+            pk.bin[J] = (unsigned char)w;
+            fill[w] += len;
+        }
+        auto key = [&](const unsigned char* bin, long long* second) {
+            int mx[32];
+            for (int w = 0; w < nb; ++w) mx[w] = -1;
+            for (int J = 0; J < NBR; ++J) mx[bin[J]] = J > mx[bin[J]] ? J : mx[bin[J]];
+            long long c = 0, s2 = 0;
+            for (int w = 0; w < nb; ++w) c += mx[w] < 0 ? 0 : (mx[w] < NBA ? mx[w] : NBA);
+            for (int J = 0; J < NBR; ++J) {
+                const int m = mx[bin[J]] < NBA ? mx[bin[J]] : NBA;
+                s2 += m - (J < NBA ? J : NBA);
+            }
+            *second = s2;
+            return c;
+        };
+        long long cur2 = 0, cur = key(pk.bin, &cur2);
+        for (;;) {
+            long long best = cur, best2 = cur2;
+            int bJ = -1, bw = -1, bJ2 = -1;
+            for (int J = 0; J < NBR; ++J) {
+                const int wa = pk.bin[J], lenJ = NBR - J;
+                for (int w = 0; w < nb; ++w) {
+                    if (w == wa) continue;
+                    if (fill[w] + lenJ <= 32) { // move J to w
+                        pk.bin[J] = (unsigned char)w;
+                        long long k2 = 0, k = key(pk.bin, &k2);
+                        pk.bin[J] = (unsigned char)wa;
+                        if (k < best || (k == best && k2 < best2)) { best = k; best2 = k2; bJ = J; bw = w; bJ2 = -1; }
+                    }
+                    for (int J2 = 0; J2 < NBR; ++J2) { // swap J and J2
+                        if (pk.bin[J2] != w) continue;
+                        const int len2 = NBR - J2;
+                        if (fill[wa] - lenJ + len2 > 32 || fill[w] - len2 + lenJ > 32) continue;
+                        pk.bin[J] = (unsigned char)w; pk.bin[J2] = (unsigned char)wa;
+                        long long k2 = 0, k = key(pk.bin, &k2);
+                        pk.bin[J] = (unsigned char)wa; pk.bin[J2] = (unsigned char)w;
+                        if (k < best || (k == best && k2 < best2)) { best = k; best2 = k2; bJ = J; bw = w; bJ2 = J2; }
+                    }
+                }
+            }
+            if (bJ < 0) break;
+            const int wa = pk.bin[bJ];
+            fill[wa] -= NBR - bJ; fill[bw] += NBR - bJ;
+            pk.bin[bJ] = (unsigned char)bw;
+            if (bJ2 >= 0) { fill[bw] -= NBR - bJ2; fill[wa] += NBR - bJ2; pk.bin[bJ2] = (unsigned char)wa; }
+            cur = best; cur2 = best2;
+        }
+        pk.nwarps = nb;
+        std::lock_guard<std::mutex> lock(mu);
+        cache.push_back(pk);
+    }
+    for (int t = 0; t < 512; ++t) tI[t] = tJ[t] = 255;
+    int fill[32] = {0};
+    for (int J = 0; J < NBR; ++J) {
+        const int w = pk.bin[J], len = NBR - J;
+        for (int e = 0; e < len; ++e) {
+            tI[w * 32 + fill[w] + e] = (unsigned char)(J + e);
+            tJ[w * 32 + fill[w] + e] = (unsigned char)J;
+        }
+        fill[w] += len;
+    }
+    *nwarps_out = pk.nwarps;
+    return true;
+}
+
 struct KktProblem {
     const double *D, *E, *Jb, *diag;
     const int* bnd;
@@ -657,24 +753,10 @@ int launch_kkt_factor(const KktProblem& q, void* stream)
     a.NBA = (q.nb + T - 1) / T; a.NBG = (q.nbd + T - 1) / T;
     const int NBR = a.NBA + a.NBG;
     if (NBR > 32) return -1; // a block column has to fit one warp
-    // first-fit packing of the block columns (NBR - J tiles each, longest first) into warps
+    // block columns -> warps (a column never straddles two): pack_columns below
     constexpr int MAXW = KktTile<T>::max_warps;
-    int fill[MAXW] = {0}, nwarps = 0;
-    for (int t = 0; t < 512; ++t) a.tI[t] = a.tJ[t] = 255;
-    for (int J = 0; J < NBR; ++J) {
-        const int len = NBR - J;
-        int w = 0;
-        while (w < nwarps && fill[w] + len > 32) ++w;
-        if (w == nwarps) {
-            if (nwarps == MAXW) return -1; // the register budget of one tile per thread
-            ++nwarps;
-        }
-        for (int e = 0; e < len; ++e) {
-            a.tI[w * 32 + fill[w] + e] = (unsigned char)(J + e);
-            a.tJ[w * 32 + fill[w] + e] = (unsigned char)J;
-        }
-        fill[w] += len;
-    }
+    int nwarps = 0;
+    if (!pack_columns(NBR, a.NBA, MAXW, a.tI, a.tJ, &nwarps)) return -1; // the register budget of one tile per thread
     int threads = nwarps * 32;
     while (8 * (q.nb + q.nbd) > KktTile<T>::nslot * threads) threads += 32; // chunk loader: nslot elements per thread
     if (threads > MAXW * 32) return -1;
