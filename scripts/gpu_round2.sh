@@ -30,4 +30,5 @@ echo "ncu kkt rc=$?"
 python scripts/dev/solver_kernels.py 4096 > gpurun_out/solver_kernels.txt 2>&1; echo "solver kernels rc=$?"
 python scripts/dev/permesh_probe.py > gpurun_out/permesh.txt 2>&1; echo "permesh rc=$?"
 python scripts/config_table.py > gpurun_out/config_table.txt 2> gpurun_out/config_table.err; echo "config table rc=$?"
+python scripts/parity_report.py > gpurun_out/parity_report.txt 2> gpurun_out/parity_report.err; echo "parity report rc=$?"
 ls -la gpurun_out | tail -20
