@@ -327,6 +327,13 @@ class BlockTridiagKKT:
             self._sp = {"J": self._csr(Rj, Cj, sel, K * mr) + (K * mr, K * nb),
                         "Jt": self._csr(Cj, Rj, sel, K * nb) + (K * nb, K * mr),
                         "H": self._csr(torch.cat([hi_, hj_[off_]]), torch.cat([hj_, hi_[off_]]), torch.cat([hs, hs[off_]]), K * nb) + (K * nb, K * nb)}
+            # the dense blocks the factorisation kernel reads, assembled by the same kernel as a gather: "row" = dense
+            # position, entries = the triplets that sum into it, x = [1] (no zero fill, no atomics: index_add_ took 2x longer)
+            zc = lambda t: torch.zeros_like(t)  # noqa: E731
+            self._sp["Jb"] = self._csr(self.j_flat, zc(self.j_flat), self.j_sel, K * mr * self.ncol) + (K * mr * self.ncol, 1)
+            self._sp["D"] = self._csr(self.hd_flat, zc(self.hd_flat), self.hd_sel, K * nb * nb) + (K * nb * nb, 1)
+            if self.he_sel.numel():
+                self._sp["E"] = self._csr(self.he_flat, zc(self.he_flat), self.he_sel, max(K - 1, 1) * nbd * nb) + (max(K - 1, 1) * nbd * nb, 1)
 
     @staticmethod
     def _csr(rows, cols, perm, nrows):
@@ -336,6 +343,12 @@ class BlockTridiagKKT:
         rowptr = torch.zeros(nrows + 1, dtype=torch.int64, device=rows.device)
         rowptr[1:] = torch.cumsum(counts, 0)
         return (rowptr.to(torch.int32).contiguous(), cols[order].to(torch.int32).contiguous(), perm[order].to(torch.int32).contiguous())
+
+    def _ones(self, B, dev):
+        o = getattr(self, "_ones_buf", None)
+        if o is None or o.shape[0] < B or o.device != dev:
+            o = self._ones_buf = torch.ones((B, 1), dtype=torch.float64, device=dev)
+        return o[:B]
 
     def _spmv(self, which, vals, x, diag=None):
         """y = A x (+ diag .* x) through lpb_batched_spmv; vals [B, nnz] triplet values, x [B, ncols] -> [B, nrows]."""
@@ -376,8 +389,11 @@ class BlockTridiagKKT:
 
     def set_jac(self, jv):
         B = jv.shape[0]
-        Jb = torch.zeros((B, self.K * self.mr * self.ncol), dtype=torch.float64, device=jv.device)
-        Jb.index_add_(1, self.j_flat, jv[:, self.j_sel])
+        if self._sp is not None and jv.is_cuda:
+            Jb = self._spmv("Jb", jv, self._ones(B, jv.device))
+        else:
+            Jb = torch.zeros((B, self.K * self.mr * self.ncol), dtype=torch.float64, device=jv.device)
+            Jb.index_add_(1, self.j_flat, jv[:, self.j_sel])
         self.Jb = Jb.view(B, self.K, self.mr, self.ncol)
         self.jv = jv  # triplet values as the kernels wrote them: the sparse products read them in place
 
@@ -594,12 +610,16 @@ class BlockTridiagKKT:
         B, K, nb, nbd, g = hv.shape[0], self.K, self.nb, self.nbd, self.gamma
         dev = hv.device
         bi = self.bnd
-        D = torch.zeros((B, K * nb * nb), dtype=torch.float64, device=dev)
-        D.index_add_(1, self.hd_flat, hv[:, self.hd_sel])
+        if self._sp is not None and hv.is_cuda:
+            D = self._spmv("D", hv, self._ones(B, dev))
+            E = self._spmv("E", hv, self._ones(B, dev)) if "E" in self._sp else torch.zeros((B, max(K - 1, 1) * nbd * nb), dtype=torch.float64, device=dev)
+        else:
+            D = torch.zeros((B, K * nb * nb), dtype=torch.float64, device=dev)
+            D.index_add_(1, self.hd_flat, hv[:, self.hd_sel])
+            E = torch.zeros((B, max(K - 1, 1) * nbd * nb), dtype=torch.float64, device=dev)
+            if self.he_sel.numel():
+                E.index_add_(1, self.he_flat, hv[:, self.he_sel])
         D = D.view(B, K, nb, nb)
-        E = torch.zeros((B, max(K - 1, 1) * nbd * nb), dtype=torch.float64, device=dev)
-        if self.he_sel.numel():
-            E.index_add_(1, self.he_flat, hv[:, self.he_sel])
         E = E.view(B, max(K - 1, 1), nbd, nb)
         di = torch.arange(nb, device=dev)
         base = D[:, :, di, di] + self.to_blocks(Sigma) + self.pad_diag
