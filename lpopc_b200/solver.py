@@ -604,6 +604,7 @@ class BlockTridiagKKT:
             return None
         if rc != 0:
             raise RuntimeError("lpb_kkt_factor failed: %d" % rc)
+        self.n_factor += 1
         return [Lall[:, i] for i in range(K)], [Call[:, i] for i in range(K - 1)], info, dw
 
     def step(self, hv, Sigma, rhs1, c, dw_last, done):
