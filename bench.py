@@ -47,6 +47,13 @@ NBUF = 4  # rotating input sets so that x is not served from L2 between steps
 # this is NOT measured in the bench run; the line says where it comes from.
 NCU_TRAFFIC_BYTES = 657005824
 NCU_TRAFFIC_SOURCE = "profiles/r02_cons_jac_full.txt (ncu --set full of this kernel on this workload; not measured in this run)"
+# FP64 issue rate of one B200 SM, measured with scripts/dev/fp64_peak.cu (independent DFMA chains, 32 warps per SM):
+# 1.81 warp instructions per cycle per SM = 33.7 TFLOP/s over 148 SMs at 1965 MHz.  The side kernels below are bound by
+# FP64 issue and latency, not by HBM, so their roofline objects carry this second bound; the executed FP64 warp
+# instructions (DADD + DMUL + DFMA + DSETP) come from the committed ncu captures, not from this run.
+FP64_WARP_INST_PER_CLK_PER_SM = 1.81
+NCU_FP64_WARP_INSTS = {"hessian": (82706437, "profiles/r02_hess_tiled_full.txt (k_hess_tiled, 4096 quadrotor instances)"),
+                       "c5": (63393752, "profiles/r02_cons_jac_rows_full.txt (k_cons_jac_rows, config 5)")}
 STRONG_TOTAL = 4096  # BASELINE config 4 as written: 4096 instances in total, sharded over the ranks
 C5_INTERVALS, C5_NODES = 10000, 10  # BASELINE config 5: synthetic ns=20 / nc=6 dynamics on 100k LGR nodes
 
@@ -256,12 +263,20 @@ def hbm_peak():
         return 6650.0, "fallback 6650 GB/s (B200_PROFILING.md)"
 
 
-def hbm_roofline(algorithmic_bytes, ms):
-    """roofline object of a side measurement: algorithmic bytes per evaluation / device time against the HBM peak."""
+def hbm_roofline(algorithmic_bytes, ms, fp64_key=None, sm_mhz=1965.0):
+    """roofline object of a side measurement: algorithmic bytes per evaluation / device time against the HBM peak, and --
+    for the compute-bound side kernels -- the FP64 issue floor of the kernel's executed FP64 instructions."""
     peak, src = hbm_peak()
     ach = algorithmic_bytes / (ms * 1e-3) / 1e9
-    return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "bytes": algorithmic_bytes, "peak_source": src,
-            "traffic": None}
+    out = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "bytes": algorithmic_bytes, "peak_source": src,
+           "traffic": None}
+    if fp64_key in NCU_FP64_WARP_INSTS:
+        insts, where = NCU_FP64_WARP_INSTS[fp64_key]
+        floor_ms = insts / (FP64_WARP_INST_PER_CLK_PER_SM * 148 * sm_mhz * 1e6) * 1e3
+        out["fp64_issue"] = {"warp_insts": insts, "warp_insts_source": where + "; not measured in this run",
+                             "peak_warp_inst_per_clk_per_sm": FP64_WARP_INST_PER_CLK_PER_SM, "peak_source": "scripts/dev/fp64_peak.cu on this pool's B200",
+                             "floor_ms": floor_ms, "frac": floor_ms / ms}
+    return out
 
 
 class _Sizes:
@@ -520,7 +535,7 @@ def main():
         hms = h0.elapsed_time(h1) / hs
         extras["hessian"] = {"value": nnz_h * nb / (hms * 1e-3), "unit": "nnz_h/s", "ms_per_eval": hms,
                              "bytes_per_eval": 8 * nb * (n + m + nnz_h), "kernel": "k_hess_tiled<LpbQuadrotor,6,3> + k_hess_endpoint",
-                             "roofline": hbm_roofline(8 * nb * (n + m + nnz_h), hms)}
+                             "roofline": hbm_roofline(8 * nb * (n + m + nnz_h), hms, "hessian")}
         del lam, d_h
         # BASELINE config 5: one synthetic ns=20 / nc=6 problem on 100k LGR nodes (76 M nnz), fused eval_g + eval_jac_g
         from lpopc_b200 import examples as _ex
@@ -550,7 +565,7 @@ def main():
         extras["c5"] = {"workload": "BASELINE config 5: synthetic ns=20/nc=6 dynamics, %d x %d = %d LGR nodes, one problem, fused eval_g+eval_jac_g"
                                     % (C5_INTERVALS, C5_NODES, C5_INTERVALS * C5_NODES),
                         "n": n5, "m": m5, "nnz_jac": nnz5, "ms_per_step": c5ms, "value": nnz5 / (c5ms * 1e-3), "unit": "nnz/s",
-                        "kernel_ms": k5ms / max(1, k5cnt), "roofline": hbm_roofline(8 * (n5 + m5 + nnz5), c5ms)}
+                        "kernel_ms": k5ms / max(1, k5cnt), "roofline": hbm_roofline(8 * (n5 + m5 + nnz5), c5ms, "c5")}
         del g5, g5_g, g5_v, x5s
 
     solves = None
