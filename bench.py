@@ -303,6 +303,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--dense-return", action="store_true", help="e2e: return the whole Jacobian head over PCIe (sparse_return = 0)")
     ap.add_argument("--no-persistent", action="store_true", help="e2e: the host rewrites the constant tail and the zero fill on every call")
+    ap.add_argument("--e2e-chunks", type=int, default=0, help="e2e: pipeline depth of the host-pointer batch call (0 = the library's default)")
     ap.add_argument("--return-mode", type=int, default=-1, help="e2e: 0 = zero-copy stores over PCIe, 1 = one strided DMA copy per run of non-zero segments; -1 = the library's default")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -429,6 +430,8 @@ def main():
     g.set_option("persistent_values", 0 if args.no_persistent else 1)
     if args.return_mode >= 0:
         g.set_option("return_mode", args.return_mode)
+    if args.e2e_chunks > 0:
+        g.set_option("e2e_chunks", args.e2e_chunks)
     for k in range(3):
         g.eval_g_jac_batch_ptr(nb, hx[k % 2].data_ptr(), hg.data_ptr(), hv.data_ptr())
     barrier()

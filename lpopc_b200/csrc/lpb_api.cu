@@ -406,6 +406,7 @@ struct lpb_handle {
     struct FillRun { size_t off, len; long long bits; };
     std::vector<FillRun> fill_runs;
     std::vector<FillRun> on_runs; // maximal runs of adjacent on-segments (return_mode 1: one strided DMA copy each)
+    int e2e_chunks = 0;           // pipeline depth of the host-pointer batch call (0: default 8)
     int return_mode = 0;          // sparse return of the head: 0 = zero-copy stores of k_return_head, 1 = one cudaMemcpy2DAsync per on-run
     size_t on_doubles = 0;   // doubles per instance that cross PCIe on the sparse path
     DevBuf<int> d_seg_off, d_seg_len, d_seg_flags;
@@ -1276,7 +1277,7 @@ int lpb_eval_g_jac_batch(lpb_handle* h, int nbatch, const double* x, double* g, 
     }
     // chunked pipeline over two streams: H2D of chunk c+1 and the kernels of chunk c overlap the
     // D2H of chunk c-1 (the D2H direction is the bottleneck of the whole call)
-    int nchunk = nbatch >= 64 ? 8 : 1;
+    int nchunk = nbatch >= 64 ? (h->e2e_chunks > 0 ? h->e2e_chunks : 8) : 1;
     if (sparse && h->return_mode == 1 && nchunk > 2) nchunk = 2; // one copy per on-run and chunk: keep the count of copies down
     const int per = (nbatch + nchunk - 1) / nchunk;
     if (nchunk > 1 && !h->pipe[0]) {
@@ -1869,6 +1870,7 @@ int lpb_set_option_int(lpb_handle* h, const char* name, int value)
     else if (!std::strcmp(name, "sweep_mode")) h->opts.sweep_mode = value;
     else if (!std::strcmp(name, "rotate_nodes")) h->opts.no_rotate = value ? 0 : 1;
     else if (!std::strcmp(name, "return_mode")) h->return_mode = value ? 1 : 0;
+    else if (!std::strcmp(name, "e2e_chunks")) h->e2e_chunks = value > 0 && value <= 64 ? value : 0;
     else if (!std::strcmp(name, "stage_values")) h->opts.stage_values = value;
     else if (!std::strcmp(name, "time_kernels")) h->time_kernels = value != 0;
     else throw ApiError(LPB_ERR_INVALID, std::string("unknown option ") + name);
