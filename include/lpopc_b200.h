@@ -234,7 +234,26 @@ int lpb_blocktri_solve_masked(int B, int K, int nb, int nbd, const double* const
 int lpb_batched_spmv(int B, int nrows, int ncols, const int* rowptr, const int* col, const int* perm, const double* vals,
                      long long val_stride, const double* x, const double* diag, double* y, void* stream);
 
-/* Tuning / introspection (not part of the reference boundary). */
+/* Tuning / introspection (not part of the reference boundary).  Options of lpb_set_option_int (default in brackets;
+ * setting any option drops the captured graphs of the single-problem fast path, which are rebuilt on the next call):
+ *   host-pointer batch calls (lpb_eval_g_jac_batch):
+ *     sparse_return [1]      only (row block, column block) segments that are not all-zero cross PCIe; the rest is
+ *                            verified on the device and written by host threads
+ *     persistent_values [0]  the caller hands the SAME values array to consecutive calls and leaves it alone in between:
+ *                            the host writes nothing after the first call (two sentinels per instance are re-checked)
+ *     auto_pin [0]           page-lock large caller arrays that come back with the same address; the caller keeps them
+ *                            alive until lpb_destroy
+ *     return_mode [0]        0: zero-copy stores of the on-segments, 1: one strided copy-engine transfer per on-run (slower)
+ *     e2e_chunks [8]         pipeline depth of the call;  host_threads [0 = half the hardware threads, at most 16]
+ *     host_fill_const [1]    constant tail [L | C] written by the host from a cached copy instead of crossing PCIe
+ *     sparse_forget          (write-only) forget the learned segment mask
+ *   single-problem TNLP calls:
+ *     fast_path [-1]         -1: on for n + m + nnz_jac <= 262144, 0: off, 1: on -- one captured graph per new x
+ *   kernels:
+ *     unroll_colours [-1], colour_split [0 = auto], pair_split [0 = auto], block [128], rotate_nodes [1], stage_values [0],
+ *     sweep_mode [0: row kernel where the functor set has the hooks, 1: per-thread sweep, 2/3: row-kernel shapes],
+ *     hess_variant (development builds), time_kernels [0] (CUDA events around the node kernels, read by lpb_kernel_time),
+ *     debug_skip (bench A/B switches) */
 int lpb_set_option_int(lpb_handle* h, const char* name, int value);
 long long lpb_kernel_launch_count(const lpb_handle* h); /* kernels launched so far */
 /* Counters: "sparse_calls" (host-pointer calls that used the sparse return), "sparse_fixups" (segments fetched
