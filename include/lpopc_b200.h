@@ -130,6 +130,8 @@ int lpb_probe_dependencies(lpb_handle* h, const double* x_guess, int* dep_out);
  * phases concatenated; interval_max: per phase K values (the quantity PhMeshRefineAlg compares with
  * "desired-relative-error").  Any output may be NULL. */
 int lpb_mesh_error(lpb_handle* h, const double* x, int* rows_out, double* rel_err, double* interval_max);
+/* The same with x and the results on the device (either output may be null); asynchronous on the handle's stream. */
+int lpb_mesh_error_dev(lpb_handle* h, const double* d_x, double* d_rel_err, double* d_interval_max);
 /* Replaces: PhMeshRefineAlg::RefineMesh / ModifySegment (LpPhMeshRefineAlg.cpp:12-99; options
  * "desired-relative-error", "Nmax", "Nmin" of LpMeshRefiner.h:67-80).  Returns the refined mesh of every phase:
  * K_out[p], then K+1 mesh points and K node counts per phase appended to mesh_out / nodes_out, whose capacities
@@ -161,6 +163,8 @@ int lpb_refine_reset(lpb_handle* h); /* forget the hp-Liu history (a new solve s
  * given, the P + 1 phase offsets into it.  total_cost (optional) = Data_->optcontrol_cost. */
 long long lpb_nlp2op_length(lpb_handle* h, long long* phase_offsets);
 int lpb_nlp2op(lpb_handle* h, const double* x, const double* lambda, double* out, double* total_cost);
+/* The same with x, lambda and the converted solution (lpb_nlp2op_length doubles) on the device; asynchronous. */
+int lpb_nlp2op_dev(lpb_handle* h, const double* d_x, const double* d_lambda, double* d_out);
 
 /* ---- batched independent instances (MPC-style; BASELINE config 4) ----------
  * nbatch instances share problem, mesh, tables and pattern; instance b uses

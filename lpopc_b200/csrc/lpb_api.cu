@@ -1560,10 +1560,11 @@ static int launch_err_relative(cudaStream_t st, const MeshErrDev& me, int P, int
 // relative error and its per-interval maximum (k_err_colmax, k_err_relative).  rel_out (sum over phases of
 // (M_p + 1) * ns doubles, phases concatenated, column-major) and imax_out (one per interval) are HOST destinations and
 // may be null: only what the caller asks for crosses PCIe.
-static void mesh_error_eval(lpb_handle* h, const double* x, double* rel_out, double* imax_out)
+// device core: tables on first use, k_mesh_error + post-processing on d_x; results stay in h->d_rel / h->d_imax
+static void mesh_error_device(lpb_handle* h, const double* d_x, size_t* total_out, int* nint_out)
 {
     need_fresh(h);
-    if (!x) throw ApiError(LPB_ERR_INVALID, "x is null");
+    if (!d_x) throw ApiError(LPB_ERR_INVALID, "x is null");
     const int P = (int)h->ph.size(), ns = h->vt->NS;
     if (!h->err_fresh) {
         long long out0 = 0;
@@ -1596,9 +1597,20 @@ static void mesh_error_eval(lpb_handle* h, const double* x, double* rel_out, dou
     h->d_colmax.reserve((size_t)P * ns);
     h->d_rel.reserve(total);
     h->d_imax.reserve((size_t)nint);
-    h2d(h, h->d_x, x, (size_t)h->pd.n);
-    note_launches(h, h->vt->mesh_error(h->pd, h->consts.data(), h->stream, h->med, nint, max_n, h->d_x.p, h->d_tem.p, h->d_abserr.p));
+    note_launches(h, h->vt->mesh_error(h->pd, h->consts.data(), h->stream, h->med, nint, max_n, d_x, h->d_tem.p, h->d_abserr.p));
     note_launches(h, launch_err_relative(h->stream, h->med, P, ns, nint, h->d_tem.p, h->d_abserr.p, h->d_colmax.p, h->d_rel.p, h->d_imax.p));
+    *total_out = total;
+    *nint_out = nint;
+}
+
+static void mesh_error_eval(lpb_handle* h, const double* x, double* rel_out, double* imax_out)
+{
+    need_fresh(h);
+    if (!x) throw ApiError(LPB_ERR_INVALID, "x is null");
+    h2d(h, h->d_x, x, (size_t)h->pd.n);
+    size_t total = 0;
+    int nint = 0;
+    mesh_error_device(h, h->d_x.p, &total, &nint);
     if (rel_out) CK(cudaMemcpyAsync(rel_out, h->d_rel.p, total * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     if (imax_out) CK(cudaMemcpyAsync(imax_out, h->d_imax.p, (size_t)nint * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -1646,6 +1658,19 @@ int lpb_mesh_error(lpb_handle* h, const double* x, int* rows_out, double* rel_er
             for (int v : h->ph[ip].nodes) M += v + 1;
             rows_out[ip] = M + 1;
         }
+    LPB_API_END(h)
+}
+
+// device-resident variant: x and the results stay on the GPU (a GPU-resident outer loop pays no PCIe copy); rel / imax
+// may be null; asynchronous on the handle's stream
+int lpb_mesh_error_dev(lpb_handle* h, const double* d_x, double* d_rel_err, double* d_interval_max)
+{
+    LPB_API_BEGIN(h)
+    size_t total = 0;
+    int nint = 0;
+    mesh_error_device(h, d_x, &total, &nint);
+    if (d_rel_err) CK(cudaMemcpyAsync(d_rel_err, h->d_rel.p, total * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    if (d_interval_max) CK(cudaMemcpyAsync(d_interval_max, h->d_imax.p, (size_t)nint * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     LPB_API_END(h)
 }
 
@@ -1785,6 +1810,17 @@ long long lpb_nlp2op_length(lpb_handle* h, long long* phase_offsets)
         return off[h->pd.P];
     } catch (const ApiError& e) { h->err = e.what(); return e.code; }
     catch (const std::exception& e) { h->err = e.what(); return LPB_ERR_INVALID; }
+}
+
+// device-resident variant of lpb_nlp2op: d_out holds lpb_nlp2op_length doubles; asynchronous on the handle's stream
+int lpb_nlp2op_dev(lpb_handle* h, const double* d_x, const double* d_lambda, double* d_out)
+{
+    LPB_API_BEGIN(h)
+    need_fresh(h);
+    if (!d_x || !d_lambda || !d_out) throw ApiError(LPB_ERR_INVALID, "bad argument");
+    ensure_scratch(h, 1);
+    note_launches(h, h->vt->nlp2op(h->pd, h->consts.data(), h->stream, d_x, d_lambda, d_out, h->d_scratch.p, nullptr));
+    LPB_API_END(h)
 }
 
 int lpb_nlp2op(lpb_handle* h, const double* x, const double* lambda, double* out, double* total_cost)

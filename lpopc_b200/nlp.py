@@ -66,6 +66,8 @@ SIGNATURES = {
     "lpb_kkt_factor": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lpb_nlp2op_length": (C.c_longlong, [_vp, C.POINTER(C.c_longlong)]),
     "lpb_nlp2op": (C.c_int, [_vp, _dp, _dp, _dp, _dp]),
+    "lpb_nlp2op_dev": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "lpb_mesh_error_dev": (C.c_int, [_vp, _vp, _vp, _vp]),
     "lpb_get_stat": (C.c_int, [_vp, C.c_char_p, C.POINTER(C.c_longlong)]),
     "lpb_kernel_time": (C.c_int, [_vp, C.c_char_p, _dp, _ip]),
     "lpb_selftest_fd_division": (C.c_int, [C.c_longlong, C.c_ulonglong, C.POINTER(C.c_longlong)]),
@@ -201,6 +203,18 @@ class TranscribedNLP:
         self._ck(self.lib.lpb_nlp2op(self.h, _d(x), _d(lam), _d(out), C.byref(tot)))
         shapes = [(int(sum(p.nodesperinterval)) + 1, len(p.statemin), len(p.controlmin), len(p.pathmin)) for p in self.op.phases]
         return unpack_nlp2op(out, shapes), tot.value
+
+    def nlp2op_dev(self, d_x, d_lam, d_out):
+        """lpb_nlp2op with device pointers (ints): the converted solution stays on the GPU (layout of lpb_nlp2op)."""
+        self._ck(self.lib.lpb_nlp2op_dev(self.h, C.c_void_p(d_x), C.c_void_p(d_lam), C.c_void_p(d_out)))
+
+    def nlp2op_length(self):
+        off = (C.c_longlong * (len(self.op.phases) + 1))()
+        return int(self.lib.lpb_nlp2op_length(self.h, off))
+
+    def mesh_error_dev(self, d_x, d_rel=None, d_imax=None):
+        """lpb_mesh_error with device pointers (ints; None = not wanted): relative error matrices and interval maxima."""
+        self._ck(self.lib.lpb_mesh_error_dev(self.h, C.c_void_p(d_x), C.c_void_p(d_rel), C.c_void_p(d_imax)))
 
     def stat(self, name):
         """Counter of the handle (lpb_get_stat): sparse_calls, sparse_fixups, sparse_on_doubles, head_doubles."""

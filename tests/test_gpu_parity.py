@@ -393,3 +393,42 @@ def test_nlp2op_end_rows_on_a_long_mesh(nlp_mod):
         full = float(adaptive.natural_spline(tau, u, np.array([1.0]))[0])
         assert abs(res[0]["control"][N, j] - full) <= RTOL * abs(full), j
         assert np.array_equal(res[0]["control"][:N, j], u)
+
+
+@pytest.mark.parametrize("name", ["launch/u5x4", "two_stage/ragged", "hypersensitive/u40x3"])
+def test_device_resident_nlp2op_and_mesh_error_equal_the_host_calls(nlp_mod, name):
+    """lpb_nlp2op_dev / lpb_mesh_error_dev (x, multipliers and results stay on the GPU: what a GPU-resident outer loop
+    calls between two solves) deliver bit for bit what the host-pointer calls deliver."""
+    import torch
+    op = cases.build(name)
+    g = nlp_mod.TranscribedNLP(op)
+    n, m = g.get_nlp_info()[:2]
+    rng = np.random.Generator(np.random.PCG64(3))
+    x = g.initial_guess() + 1e-3 * rng.standard_normal(n)
+    lam = rng.standard_normal(m)
+    dev = torch.device("cuda")
+    dx, dl = torch.from_numpy(x).to(dev), torch.from_numpy(lam).to(dev)
+    # converted solution
+    host, _ = g.nlp2op(x, lam)
+    L = g.nlp2op_length()
+    d_out = torch.full((L,), float("nan"), dtype=torch.float64, device=dev)
+    g.nlp2op_dev(dx.data_ptr(), dl.data_ptr(), d_out.data_ptr())
+    torch.cuda.synchronize()
+    shapes = [(int(sum(p.nodesperinterval)) + 1, len(p.statemin), len(p.controlmin), len(p.pathmin)) for p in op.phases]
+    devres = nlp_mod.unpack_nlp2op(d_out.cpu().numpy(), shapes)
+    for a, b in zip(host, devres):
+        for key in ("time", "state", "control", "costate", "pathmult", "hamiltonian"):
+            assert np.array_equal(a[key], b[key], equal_nan=True), key
+        assert a["mayer"] == b["mayer"] and a["lagrange"] == b["lagrange"]
+    # mesh error
+    rel, imax = g.mesh_error(x)
+    nrel, nint = sum(r.size for r in rel), sum(v.size for v in imax)
+    d_rel = torch.full((nrel,), float("nan"), dtype=torch.float64, device=dev)
+    d_imax = torch.full((nint,), float("nan"), dtype=torch.float64, device=dev)
+    g.mesh_error_dev(dx.data_ptr(), d_rel.data_ptr(), d_imax.data_ptr())
+    torch.cuda.synchronize()
+    flat = np.concatenate([r.T.reshape(-1) for r in rel])  # per phase: column-major rows x ns
+    assert np.array_equal(d_rel.cpu().numpy(), flat) and np.array_equal(d_imax.cpu().numpy(), np.concatenate(imax))
+    g.mesh_error_dev(dx.data_ptr(), None, d_imax.data_ptr())  # interval maxima only
+    torch.cuda.synchronize()
+    assert np.array_equal(d_imax.cpu().numpy(), np.concatenate(imax))
