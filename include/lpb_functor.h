@@ -18,6 +18,12 @@
  * assume it).  Here that requirement is the interface: a functor sees one node.
  * `phase` is 1-based like `phase_num_` (LpNLPWrapper.cpp:107).
  *
+ * One `link` for all linkage pairs, with the same number of links per pair (the C ABI rejects unequal counts): the
+ * reference cannot tell its user function reliably WHICH pair it is asked about -- the constraint evaluation leaves
+ * SolLink::ipair unset and passes 0-based phase numbers (LpNLPWrapper.cpp:195-205) while the Jacobian and Hessian
+ * paths pass ipair + 1 and 1-based phase numbers (LpNLPWrapper.cpp:420-426, LpHessian.cpp:1046-1052) -- so only a
+ * pair-independent link function is well defined there, which is what its own launch example uses.
+ *
  * A functor set is a plain struct with compile-time sizes shared by all phases
  * (NS states, NC controls, NPATH path constraints; NE_MAX/NL_MAX upper bounds for
  * events per phase / links per pair) and a POD `Consts` block of doubles that the
