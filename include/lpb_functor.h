@@ -59,6 +59,14 @@
  * once per (node, row s in [0, NS + NPATH)): nd.x(j), nd.u(j), nd.t the node's variables, nd.perturbed(cc) = vp of
  * variable cc, nd.pre(cc, i) the values sweep_pre stored; k as in dae_sweep (begin / state_row / path_row for row s
  * only).  Returns the row's base value f_s (path rows: the path value).  Same exactness contract as dae_sweep.
+ *
+ * Optional members `pre_value` / `dae_with_pre` (flagged by `static constexpr bool HAS_DAE_PRE = true`): for the
+ * second-difference Hessian of dynamics that apply an expensive univariate function to each state,
+ *     static double pre_value(c, phase, j, v)                       that function of state j at the value v
+ *     static void dae_with_pre(c, phase, t, x, u, pv, f, path)      dae() with pv[j] in place of pre_value(.., j, x[j])
+ * The kernel (k_hess_nodes) evaluates pre_value at the three values a state takes among the stencil points and passes
+ * the matching one per state; dae_with_pre must perform dae()'s operations on them in dae()'s order (bit-identical
+ * values: the parity tests compare against the oracle, which calls dae()).
  */
 #ifndef LPB_FUNCTOR_H
 #define LPB_FUNCTOR_H

@@ -29,6 +29,25 @@ struct LpbSynthetic20 {
             f[s] = acc - 0.1 * ((x[s] * x[s]) * x[s]);
         }
     }
+    /* Optional hook (lpb_functor.h "dae_with_pre"): the second-difference Hessian evaluates dae() at 378 points per node
+     * that differ from the node's values in one or two variables; the expensive univariate part of this dynamics --
+     * tanh(x_j) -- takes three values per state there (x_j, x_j + h_j, (x_j + h_j) + h_j), so the kernel computes those
+     * once per node through pre_value and hands the right one per state to dae_with_pre: the same operations as dae()
+     * on the same operands, minus 20 tanh per point. */
+    static constexpr bool HAS_DAE_PRE = true;
+    LPB_HD static double pre_value(const Consts&, int, int, double v) { return lpb_det_tanh(v); }
+    LPB_HD static void dae_with_pre(const Consts& C, int, double, const double* x, const double* u, const double* pv, double* f, double*)
+    {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            double acc = 0.0;
+#pragma unroll
+            for (int j = 0; j < NS; ++j) acc = acc + C.A[s * NS + j] * pv[j];
+#pragma unroll
+            for (int j = 0; j < NC; ++j) acc = acc + C.B[s * NC + j] * u[j];
+            f[s] = acc - 0.1 * ((x[s] * x[s]) * x[s]);
+        }
+    }
     /* Optional hook (lpb_functor.h "dae_sweep"): the base evaluation and every single-variable perturbation
      * the forward-difference Jacobian needs, in ONE pass that shares work between them.  Perturbing x_j changes
      * only tanh(x_j) and the j-th term onwards of each row sum, so the sum over the terms before j (pre[s],

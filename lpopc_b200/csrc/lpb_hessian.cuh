@@ -136,11 +136,38 @@ __device__ __forceinline__ void hess_store_pair(const PhaseDev& ph, const HessNo
 // generic pair body: run-time variable indices, every function row, IEEE quotients.  This is the
 // arithmetic definition of the node part (the tiled kernel below must match it bit for bit).
 // ------------------------------------------------------------------------------------------
+template <class P, class = void>
+struct has_dae_pre : std::false_type {};
+template <class P>
+struct has_dae_pre<P, std::enable_if_t<P::HAS_DAE_PRE>> : std::true_type {};
+
+// dae() at a stencil point whose variables a and b (b = -1: none) are perturbed; with the functor set's pre-value hook
+// and the node's table pv[times perturbed][state] the expensive univariate part is looked up instead of recomputed
+template <class P>
+__device__ __forceinline__ void hess_dae(const typename P::Consts& C, int phase1, double t, const double* xq, const double* uq,
+                                         const double (*pv)[Dim<P>::NSa], int a, int b, double* f, double* c)
+{
+    if constexpr (has_dae_pre<P>::value) {
+        if (pv != nullptr) {
+            double pq[Dim<P>::NSa];
+#pragma unroll
+            for (int j = 0; j < Dim<P>::NS; ++j) {
+                const int cnt = (a == j ? 1 : 0) + (b == j ? 1 : 0);
+                pq[j] = cnt == 2 ? pv[2][j] : (cnt == 1 ? pv[1][j] : pv[0][j]);
+            }
+            P::dae_with_pre(C, phase1, t, xq, uq, pq, f, c);
+            return;
+        }
+    }
+    P::dae(C, phase1, t, xq, uq, f, c);
+}
+
 template <class P>
 __device__ __forceinline__ void hess_pair_generic(const ProblemDev& pd, const typename P::Consts& C, const HessNode<P>& nd, int a, double ha,
                                                   const double* xa, const double* ua, double ta, const double* fa, const double* ca,
                                                   double La, int b, double* __restrict__ scr, long long gid, long long tot,
-                                                  const double* fb_cached = nullptr, const double* cb_cached = nullptr, double Lb_cached = 0.0)
+                                                  const double* fb_cached = nullptr, const double* cb_cached = nullptr, double Lb_cached = 0.0,
+                                                  const double (*pv)[Dim<P>::NSa] = nullptr)
 {
     typedef Dim<P> D;
     constexpr int T = D::NS + D::NC; // index of the time variable
@@ -173,7 +200,7 @@ __device__ __forceinline__ void hess_pair_generic(const ProblemDev& pd, const ty
 #pragma unroll
         for (int j = 0; j < D::NC; ++j) uq[j] = (b == D::NS + j) ? nd.us[j] + hb : nd.us[j];
         const double tq = (b == T) ? nd.t + hb : nd.t;
-        P::dae(C, p + 1, tq, xq, uq, fb, cb);
+        hess_dae<P>(C, p + 1, tq, xq, uq, pv, b, -1, fb, cb);
         Lb = P::lagrange(C, p + 1, tq, xq, uq);
     }
     // point (a then b): start from the a-perturbed point, add h_b to variable b
@@ -182,7 +209,7 @@ __device__ __forceinline__ void hess_pair_generic(const ProblemDev& pd, const ty
 #pragma unroll
     for (int j = 0; j < D::NC; ++j) uq[j] = (b == D::NS + j) ? ua[j] + hb : ua[j];
     const double tq2 = (b == T) ? ta + hb : ta;
-    P::dae(C, p + 1, tq2, xq, uq, fab, cab);
+    hess_dae<P>(C, p + 1, tq2, xq, uq, pv, a, b, fab, cab);
     const double Lab = P::lagrange(C, p + 1, tq2, xq, uq);
     const double den = ha * hb;
     const FdDiv dvp(den); // one reciprocal per pair, IEEE-exact quotients (lpb_kernels.cuh)
@@ -224,6 +251,19 @@ __device__ __forceinline__ void hess_range_generic(const ProblemDev& pd, const t
     constexpr int T = D::NS + D::NC;
     constexpr int NCACHE = CACHE ? D::NCOL : 1;
     double fsv[NCACHE][D::NSa], csv[NCACHE][D::NPa], Lsv[NCACHE];
+    constexpr bool PRE = CACHE && has_dae_pre<P>::value;
+    double pvs[PRE ? 3 : 1][D::NSa];
+    const double (*pv)[D::NSa] = nullptr;
+    if constexpr (PRE) { // the three values a state takes among the stencil points: v, v + h, (v + h) + h
+#pragma unroll 1
+        for (int j = 0; j < D::NS; ++j) {
+            const double v = nd.xs[j], hj = nd.tol * (1 + fabs(v));
+            pvs[0][j] = P::pre_value(C, nd.p + 1, j, v);
+            pvs[1][j] = P::pre_value(C, nd.p + 1, j, v + hj);
+            pvs[2][j] = P::pre_value(C, nd.p + 1, j, (v + hj) + hj);
+        }
+        pv = pvs;
+    }
     for (int a = a0; a < a1; ++a) {
         const double ha = nd.tol * (1 + fabs(hess_var(nd, a)));
         double xa[D::NSa], ua[D::NCa], fa[D::NSa], ca[D::NPa];
@@ -232,7 +272,7 @@ __device__ __forceinline__ void hess_range_generic(const ProblemDev& pd, const t
 #pragma unroll
         for (int j = 0; j < D::NC; ++j) ua[j] = (a == D::NS + j) ? nd.us[j] + ha : nd.us[j];
         const double ta = (a == T) ? nd.t + ha : nd.t;
-        P::dae(C, nd.p + 1, ta, xa, ua, fa, ca);
+        hess_dae<P>(C, nd.p + 1, ta, xa, ua, pv, a, -1, fa, ca);
         const double La = P::lagrange(C, nd.p + 1, ta, xa, ua);
         const int bend = b1 < a + 1 ? b1 : a + 1;
         if constexpr (CACHE) {
@@ -242,8 +282,8 @@ __device__ __forceinline__ void hess_range_generic(const ProblemDev& pd, const t
             for (int s = 0; s < D::NP; ++s) csv[a][s] = ca[s];
             Lsv[a] = La;
             for (int b = b0; b < bend; ++b) {
-                if (b >= a0) hess_pair_generic<P>(pd, C, nd, a, ha, xa, ua, ta, fa, ca, La, b, scr, gid, tot, fsv[b], csv[b], Lsv[b]);
-                else hess_pair_generic<P>(pd, C, nd, a, ha, xa, ua, ta, fa, ca, La, b, scr, gid, tot);
+                if (b >= a0) hess_pair_generic<P>(pd, C, nd, a, ha, xa, ua, ta, fa, ca, La, b, scr, gid, tot, fsv[b], csv[b], Lsv[b], pv);
+                else hess_pair_generic<P>(pd, C, nd, a, ha, xa, ua, ta, fa, ca, La, b, scr, gid, tot, nullptr, nullptr, 0.0, pv);
             }
         } else {
             for (int b = b0; b < bend; ++b) hess_pair_generic<P>(pd, C, nd, a, ha, xa, ua, ta, fa, ca, La, b, scr, gid, tot);
