@@ -419,6 +419,7 @@ struct lpb_handle {
     DevBuf<long long> d_seg_fill;
     DevBuf<unsigned char> d_seg_on;
     int* h_seg_flags = nullptr; // pinned
+    size_t h_seg_flags_cap = 0; // ints
     long long sparse_calls = 0, sparse_fixups = 0;
     // option "persistent_values": the caller hands the SAME values array to consecutive batch calls and does not
     // write to it in between (IPOPT's TNLPAdapter does exactly that with its jac_g array).  Everything the host
@@ -649,8 +650,11 @@ static void refresh(lpb_handle* h)
         h->d_seg_on.upload(h->seg_on, h->stream);
         h->d_seg_fill.upload(h->seg_fill, h->stream);
         h->d_seg_flags.reserve(h->seg_off.size() + 1);
-        if (h->h_seg_flags) { cudaFreeHost(h->h_seg_flags); h->h_seg_flags = nullptr; }
-        CK(cudaMallocHost((void**)&h->h_seg_flags, (h->seg_off.size() + 1) * sizeof(int)));
+        if (h->seg_off.size() + 1 > h->h_seg_flags_cap) { // page-locked allocations cost milliseconds: grow only
+            if (h->h_seg_flags) { cudaFreeHost(h->h_seg_flags); h->h_seg_flags = nullptr; h->h_seg_flags_cap = 0; }
+            CK(cudaMallocHost((void**)&h->h_seg_flags, (h->seg_off.size() + 1) * sizeof(int)));
+            h->h_seg_flags_cap = h->seg_off.size() + 1;
+        }
     }
     CK(cudaStreamSynchronize(h->stream));
     {
