@@ -13,16 +13,8 @@ x = torch.from_numpy(g.initial_guess() + 1e-3 * rng.standard_normal(n)).cuda()
 lam = torch.from_numpy(rng.standard_normal(m)).cuda()
 sg = torch.ones(1, dtype=torch.float64, device="cuda")
 dh = torch.empty(nnzh, dtype=torch.float64, device="cuda")
-for _ in range(2):
-    g.eval_h_dev(1, x.data_ptr(), sg.data_ptr(), lam.data_ptr(), dh.data_ptr())
-torch.cuda.synchronize()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-for _ in range(5):
-    g.eval_h_dev(1, x.data_ptr(), sg.data_ptr(), lam.data_ptr(), dh.data_ptr())
-e1.record(); torch.cuda.synchronize()
-ms = e0.elapsed_time(e1) / 5
-print("n=%d m=%d nnz_h=%d  eval_h %.3f ms  %.3e nnz_h/s  %.1f GB/s algorithmic (8 (n + m + nnz_h))" % (n, m, nnzh, ms, nnzh / (ms * 1e-3), 8 * (n + m + nnzh) / (ms * 1e-3) / 1e9))
+g.eval_h_dev(1, x.data_ptr(), sg.data_ptr(), lam.data_ptr(), dh.data_ptr())
+print("n=%d m=%d nnz_h=%d" % (n, m, nnzh))
 import time
 torch.cuda.synchronize(); t0 = time.perf_counter()
 g.eval_h_dev(1, x.data_ptr(), sg.data_ptr(), lam.data_ptr(), dh.data_ptr())
